@@ -1,0 +1,440 @@
+// e4t_b200 — tcgen05 GEMM engine (sm_100a).
+//
+// One persistent, warp-specialised kernel serves every dense contraction on the E4T hot path:
+//   * linear layers   Y[M,N] = A[M,K] · B[N,K]^T            (both operands K-major, e.g. F.linear;
+//                                                            reference call sites cross_attention.py:506-518,534,
+//                                                            attention.py:429 (GEGLU proj), transformer_2d.py proj_in/out)
+//   * weight-gradient  dW[C,R] = dY[m,C]^T · X[m,R]          (both operands MN-major, split-K, fp32 atomic accumulate)
+//   * input-gradient   dX[M,K] = dY[M,N] · W[N,K]            (A K-major, B MN-major)
+//   * 3x3 convolution  (implicit GEMM over NHWC, 9 taps x Cin/64 K-chunks, halo by TMA out-of-bounds zero fill;
+//                       diffusers ResnetBlock2D conv1/conv2, Upsample2D.conv, Downsample2D.conv)
+//
+// Structure (per CTA, 256 threads): warp0 = TMA producer, warp1 = MMA issuer (one thread issues tcgen05.mma),
+// warp2 = TMEM allocator, warps4-7 = epilogue (TMEM -> registers -> global).  smem ring of `stages`
+// {A 128x64, B BNx64} bf16 tiles (SWIZZLE_128B), two TMEM accumulator stages of 256 columns so the epilogue of
+// tile i overlaps the MMAs of tile i+1.
+#include "common.cuh"
+
+struct GemmArgs {
+  int M, N, K, batch;
+  int BN, m_tiles, n_tiles, splits, kchunks, kper, stages;
+  int a_mn, b_mn, a_batched, b_batched;
+  // implicit 3x3 convolution
+  int conv, H, W, BH, BB, cin_chunks, cout;
+  // epilogue
+  void* out;
+  int out_mode;  // 0 = bf16 store, 1 = fp32 store, 2 = fp32 atomic add
+  long long ldo, out_bstride;
+  const float* bias;      // [N] or null
+  const float* rowgroup;  // [M / rows_per_group][N] fp32 (e.g. time-embedding add per image) or null
+  int rows_per_group;
+  const bf16* residual;  // [M][ldr] bf16 or null
+  long long ldr, res_bstride;
+  float alpha;
+};
+
+static constexpr int kBM = 128;
+static constexpr int kBK = 64;
+static constexpr int kATileBytes = kBM * kBK * 2;  // 16 KiB
+static constexpr int kThreads = 256;
+
+__global__ void __launch_bounds__(kThreads, 1)
+e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                const GemmArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // align dynamic smem to 1024 B (SWIZZLE_128B atoms)
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int b_tile_bytes = g.BN * kBK * 2;
+  const int stage_bytes = kATileBytes + b_tile_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)g.stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + g.stages;
+  uint64_t* tfull_bar = empty_bar + g.stages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < g.stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const long total_tiles = (long)g.batch * g.splits * g.m_tiles * g.n_tiles;
+
+  if (warp == 0) {
+    // ===================== TMA producer (one thread) =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int n_t = (int)(t % g.n_tiles);
+        long r = t / g.n_tiles;
+        const int m_t = (int)(r % g.m_tiles);
+        r /= g.m_tiles;
+        const int sp = (int)(r % g.splits);
+        const int bz = (int)(r / g.splits);
+        const int m0 = m_t * kBM, n0 = n_t * g.BN;
+        const int kc0 = sp * g.kper;
+        const int kc1 = min(g.kchunks, kc0 + g.kper);
+        int cb0 = 0, ch0 = 0;
+        if (g.conv) {
+          const int img = g.H * g.W;
+          cb0 = m0 / img;
+          ch0 = (m0 % img) / g.W;
+        }
+        for (int kc = kc0; kc < kc1; ++kc) {
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          uint8_t* sA = smem + (size_t)s * stage_bytes;
+          uint8_t* sB = sA + kATileBytes;
+          mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
+          if (g.conv) {
+            const int tap = kc / g.cin_chunks, cc = kc % g.cin_chunks;
+            const int dy = tap / 3, dx = tap % 3;
+            tma_load_4d(sA, &mapA, &full_bar[s], cc * kBK, dx - 1, ch0 + dy - 1, cb0);
+            tma_load_2d(sB, &mapB, &full_bar[s], cc * kBK, tap * g.cout + n0);
+          } else {
+            const int ab = g.a_batched ? bz : 0, bb = g.b_batched ? bz : 0;
+            if (!g.a_mn) {
+              tma_load_3d(sA, &mapA, &full_bar[s], kc * kBK, m0, ab);
+            } else {
+              tma_load_3d(sA, &mapA, &full_bar[s], m0, kc * kBK, ab);
+              tma_load_3d(sA + 8192, &mapA, &full_bar[s], m0 + 64, kc * kBK, ab);
+            }
+            if (!g.b_mn) {
+              tma_load_3d(sB, &mapB, &full_bar[s], kc * kBK, n0, bb);
+            } else {
+              for (int i = 0; i < g.BN / 64; ++i)
+                tma_load_3d(sB + i * 8192, &mapB, &full_bar[s], n0 + 64 * i, kc * kBK, bb);
+            }
+          }
+          if (++s == g.stages) {
+            s = 0;
+            ph ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16((uint32_t)g.BN, g.a_mn != 0, g.b_mn != 0);
+      int s = 0, as = 0;
+      uint32_t ph = 0, aph = 0;
+      for (long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        long r = t / g.n_tiles / g.m_tiles;
+        const int sp = (int)(r % g.splits);
+        const int kc0 = sp * g.kper;
+        const int kc1 = min(g.kchunks, kc0 + g.kper);
+        mbar_wait(&tempty_bar[as], aph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)as * 256u;
+        for (int kc = kc0; kc < kc1; ++kc) {
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sA = smem_u32(smem + (size_t)s * stage_bytes);
+          const uint32_t sB = sA + kATileBytes;
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            const uint64_t da = g.a_mn ? umma_desc(sA + k * 2048, 8192, 1024) : umma_desc(sA + k * 32, 16, 1024);
+            const uint64_t db = g.b_mn ? umma_desc(sB + k * 2048, 8192, 1024) : umma_desc(sB + k * 32, 16, 1024);
+            umma_bf16(d_tmem, da, db, idesc, (kc > kc0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);  // frees the smem stage when these MMAs retire
+          if (++s == g.stages) {
+            s = 0;
+            ph ^= 1u;
+          }
+        }
+        umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
+        as ^= 1;
+        if (as == 0) aph ^= 1u;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (128 threads, one accumulator row each) =====================
+    const int ew = warp - 4;  // == warp % 4 -> TMEM lane quadrant
+    const int row = ew * 32 + lane;
+    int as = 0;
+    uint32_t aph = 0;
+    for (long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int n_t = (int)(t % g.n_tiles);
+      long r = t / g.n_tiles;
+      const int m_t = (int)(r % g.m_tiles);
+      r /= g.m_tiles;
+      const int bz = (int)(r / g.splits);
+      const int m = m_t * kBM + row;
+      const int n0 = n_t * g.BN;
+      mbar_wait(&tfull_bar[as], aph);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (uint32_t)as * 256u + ((uint32_t)(ew * 32) << 16);
+      const bool row_ok = m < g.M;
+      const float* rg = (g.rowgroup && row_ok) ? g.rowgroup + (long long)(m / g.rows_per_group) * g.N : nullptr;
+      const bf16* res = (g.residual && row_ok) ? g.residual + (long long)bz * g.res_bstride + (long long)m * g.ldr
+                                               : nullptr;
+      for (int c = 0; c < g.BN; c += 32) {
+        uint32_t v[32];
+        __syncwarp();
+        tmem_ld32(t_row + (uint32_t)c, v);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int n = n0 + c + q * 8;
+          if (n >= g.N) break;
+          float f[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[q * 8 + j]) * g.alpha;
+          const bool full8 = (n + 8 <= g.N);
+          if (full8) {
+            if (g.bias) {
+              const float4 b0 = *reinterpret_cast<const float4*>(g.bias + n);
+              const float4 b1 = *reinterpret_cast<const float4*>(g.bias + n + 4);
+              f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+              f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+            }
+            if (rg) {
+              const float4 b0 = *reinterpret_cast<const float4*>(rg + n);
+              const float4 b1 = *reinterpret_cast<const float4*>(rg + n + 4);
+              f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+              f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+            }
+            if (res) {
+              const uint4 rv = *reinterpret_cast<const uint4*>(res + n);
+              const float2 r0 = unpack_bf16(rv.x), r1 = unpack_bf16(rv.y), r2 = unpack_bf16(rv.z),
+                           r3 = unpack_bf16(rv.w);
+              f[0] += r0.x; f[1] += r0.y; f[2] += r1.x; f[3] += r1.y;
+              f[4] += r2.x; f[5] += r2.y; f[6] += r3.x; f[7] += r3.y;
+            }
+            if (g.out_mode == 0) {
+              bf16* o = reinterpret_cast<bf16*>(g.out) + (long long)bz * g.out_bstride + (long long)m * g.ldo + n;
+              uint4 ov;
+              ov.x = pack_bf16(f[0], f[1]); ov.y = pack_bf16(f[2], f[3]);
+              ov.z = pack_bf16(f[4], f[5]); ov.w = pack_bf16(f[6], f[7]);
+              *reinterpret_cast<uint4*>(o) = ov;
+            } else if (g.out_mode == 1) {
+              float* o = reinterpret_cast<float*>(g.out) + (long long)bz * g.out_bstride + (long long)m * g.ldo + n;
+              *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
+              *reinterpret_cast<float4*>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
+            } else {
+              float* o = reinterpret_cast<float*>(g.out) + (long long)bz * g.out_bstride + (long long)m * g.ldo + n;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) atomicAdd(o + j, f[j]);
+            }
+          } else {
+            for (int j = 0; j < 8 && n + j < g.N; ++j) {
+              float x = f[j];
+              if (g.bias) x += g.bias[n + j];
+              if (rg) x += rg[n + j];
+              if (res) x += __bfloat162float(res[n + j]);
+              const long long off = (long long)bz * g.out_bstride + (long long)m * g.ldo + n + j;
+              if (g.out_mode == 0) reinterpret_cast<bf16*>(g.out)[off] = __float2bfloat16(x);
+              else if (g.out_mode == 1) reinterpret_cast<float*>(g.out)[off] = x;
+              else atomicAdd(reinterpret_cast<float*>(g.out) + off, x);
+            }
+          }
+        }
+        }  // row_ok
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[as]);
+      as ^= 1;
+      if (as == 0) aph ^= 1u;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------
+static int g_num_sms = 0;
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+static int pick_bn(int N, long m_tiles_x_batch, bool b_mn, int force_bn) {
+  if (force_bn > 0) return force_bn;
+  const int step = b_mn ? 64 : 32;
+  int best = 0;
+  double best_score = -1.0;
+  for (int bn = 256; bn >= 64; bn -= step) {
+    const int tiles_n = cdiv(N, bn);
+    const double eff = (double)N / ((double)tiles_n * bn);
+    const double tiles = (double)tiles_n * (double)m_tiles_x_batch;
+    const double sms = (double)num_sms();
+    // wave efficiency of a persistent launch
+    const double waves = tiles / sms;
+    const double wave_eff = waves / (double)((long)((tiles + sms - 1) / sms));
+    // wider tiles are a little cheaper per flop (A-tile reuse); tiny preference
+    const double width = 0.9 + 0.1 * bn / 256.0;
+    const double score = eff * wave_eff * width;
+    if (score > best_score + 1e-9) {
+      best_score = score;
+      best = bn;
+    }
+  }
+  return best;
+}
+
+static int launch_gemm(const CUtensorMap& mA, const CUtensorMap& mB, GemmArgs& g, cudaStream_t stream) {
+  const int stage_bytes = kATileBytes + g.BN * kBK * 2;
+  int stages = (196 * 1024) / stage_bytes;
+  if (stages > 8) stages = 8;
+  if (stages > g.kper) stages = g.kper < 2 ? 2 : g.kper;
+  g.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 4) * sizeof(uint64_t) + 16 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    E4T_CUDA(cudaFuncSetAttribute(e4t_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const long total = (long)g.batch * g.splits * g.m_tiles * g.n_tiles;
+  int grid = (int)(total < num_sms() ? total : num_sms());
+  if (grid < 1) return 0;
+  e4t_gemm_kernel<<<grid, kThreads, smem, stream>>>(mA, mB, g);
+  E4T_COUNT_LAUNCH();
+  E4T_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int e4t_gemm_bf16(const void* A, const void* B, void* out, int M, int N, int K, int batch, int a_mn,
+                             int b_mn, long long lda, long long ldb, long long a_bstride, long long b_bstride,
+                             int out_mode, long long ldo, long long out_bstride, const float* bias,
+                             const float* rowgroup, int rows_per_group, const void* residual, long long ldr,
+                             long long res_bstride, float alpha, int splits, int force_bn, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  E4T_CHECK(M > 0 && N > 0 && K > 0 && batch > 0, "e4t_gemm_bf16: bad dims M=%d N=%d K=%d batch=%d", M, N, K, batch);
+  E4T_CHECK((lda % 8) == 0 && (ldb % 8) == 0, "e4t_gemm_bf16: leading strides must be multiples of 8 elements");
+  E4T_CHECK(((uintptr_t)A % 16) == 0 && ((uintptr_t)B % 16) == 0, "e4t_gemm_bf16: operands must be 16-byte aligned");
+  E4T_CHECK(out_mode >= 0 && out_mode <= 2, "e4t_gemm_bf16: bad out_mode");
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.M = M; g.N = N; g.K = K; g.batch = batch;
+  g.a_mn = a_mn; g.b_mn = b_mn;
+  g.a_batched = (a_bstride != 0); g.b_batched = (b_bstride != 0);
+  g.m_tiles = cdiv(M, kBM);
+  g.kchunks = cdiv(K, kBK);
+  if (splits < 1) splits = 1;
+  if (splits > g.kchunks) splits = g.kchunks;
+  g.kper = cdiv(g.kchunks, splits);
+  g.splits = cdiv(g.kchunks, g.kper);  // no empty split
+  g.BN = pick_bn(N, (long)g.m_tiles * batch * g.splits, b_mn != 0, force_bn);
+  E4T_CHECK(g.BN >= 32 && g.BN <= 256 && (g.BN % (b_mn ? 64 : 32)) == 0, "e4t_gemm_bf16: bad BN %d", g.BN);
+  g.n_tiles = cdiv(N, g.BN);
+  E4T_CHECK(g.splits == 1 || out_mode == 2, "e4t_gemm_bf16: split-K requires atomic fp32 output");
+  g.out = out; g.out_mode = out_mode; g.ldo = ldo; g.out_bstride = out_bstride;
+  g.bias = bias; g.rowgroup = rowgroup; g.rows_per_group = rows_per_group > 0 ? rows_per_group : 1;
+  g.residual = (const bf16*)residual; g.ldr = ldr; g.res_bstride = res_bstride;
+  g.alpha = alpha;
+
+  CUtensorMap mA, mB;
+  {
+    const uint64_t nb = g.a_batched ? (uint64_t)batch : 1;
+    const uint64_t bs = g.a_batched ? (uint64_t)a_bstride : (uint64_t)lda * (a_mn ? K : M);
+    if (!a_mn) {
+      uint64_t dims[3] = {(uint64_t)K, (uint64_t)M, nb};
+      uint64_t str[2] = {(uint64_t)lda * 2, bs * 2};
+      uint32_t box[3] = {kBK, kBM, 1};
+      if (int e = e4t_tmap_encode(&mA, A, 3, dims, str, box, 2)) return e;
+    } else {
+      uint64_t dims[3] = {(uint64_t)M, (uint64_t)K, nb};
+      uint64_t str[2] = {(uint64_t)lda * 2, bs * 2};
+      uint32_t box[3] = {64, kBK, 1};
+      if (int e = e4t_tmap_encode(&mA, A, 3, dims, str, box, 2)) return e;
+    }
+  }
+  {
+    const uint64_t nb = g.b_batched ? (uint64_t)batch : 1;
+    const uint64_t bs = g.b_batched ? (uint64_t)b_bstride : (uint64_t)ldb * (b_mn ? K : N);
+    if (!b_mn) {
+      uint64_t dims[3] = {(uint64_t)K, (uint64_t)N, nb};
+      uint64_t str[2] = {(uint64_t)ldb * 2, bs * 2};
+      uint32_t box[3] = {kBK, (uint32_t)g.BN, 1};
+      if (int e = e4t_tmap_encode(&mB, B, 3, dims, str, box, 2)) return e;
+    } else {
+      uint64_t dims[3] = {(uint64_t)N, (uint64_t)K, nb};
+      uint64_t str[2] = {(uint64_t)ldb * 2, bs * 2};
+      uint32_t box[3] = {64, kBK, 1};
+      if (int e = e4t_tmap_encode(&mB, B, 3, dims, str, box, 2)) return e;
+    }
+  }
+  return launch_gemm(mA, mB, g, stream);
+}
+
+// x: NHWC bf16 [B][H][W][Cin];  w: bf16 [9][Cout][Cin] (tap = ky*3+kx);  out: [B*H*W][Cout] (NHWC)
+// stride 1, pad 1.  bias fp32 [Cout]; rowgroup fp32 [B][Cout] (time-embedding projection) ; residual bf16 NHWC.
+extern "C" int e4t_conv3x3_bf16(const void* x, const void* w, void* out, int B, int H, int W, int Cin, int Cout,
+                                int out_mode, const float* bias, const float* rowgroup, const void* residual,
+                                int force_bn, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  E4T_CHECK(Cin % 64 == 0, "e4t_conv3x3_bf16: Cin must be a multiple of 64 (got %d)", Cin);
+  E4T_CHECK(W <= 128 && (128 % W) == 0, "e4t_conv3x3_bf16: W must divide 128 (got %d)", W);
+  E4T_CHECK(out_mode == 0 || out_mode == 1, "e4t_conv3x3_bf16: bad out_mode");
+  const int img = H * W;
+  int BH, BB;
+  if (img >= 128) {
+    BB = 1;
+    BH = 128 / W;
+    E4T_CHECK(H % BH == 0, "e4t_conv3x3_bf16: H=%d not a multiple of tile height %d", H, BH);
+  } else {
+    E4T_CHECK(128 % img == 0, "e4t_conv3x3_bf16: H*W must divide 128");
+    BB = 128 / img;
+    BH = H;
+  }
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.M = B * img; g.N = Cout; g.K = Cin; g.batch = 1;
+  g.conv = 1; g.H = H; g.W = W; g.BH = BH; g.BB = BB; g.cin_chunks = Cin / 64; g.cout = Cout;
+  g.m_tiles = cdiv(g.M, kBM);
+  g.kchunks = 9 * g.cin_chunks;
+  g.kper = g.kchunks; g.splits = 1;
+  g.BN = pick_bn(Cout, g.m_tiles, false, force_bn);
+  g.n_tiles = cdiv(Cout, g.BN);
+  g.out = out; g.out_mode = out_mode; g.ldo = Cout; g.out_bstride = 0;
+  g.bias = bias; g.rowgroup = rowgroup; g.rows_per_group = img;
+  g.residual = (const bf16*)residual; g.ldr = Cout; g.res_bstride = 0;
+  g.alpha = 1.f;
+  CUtensorMap mA, mB;
+  {
+    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)img * Cin * 2};
+    uint32_t box[4] = {kBK, (uint32_t)W, (uint32_t)BH, (uint32_t)BB};
+    if (int e = e4t_tmap_encode(&mA, x, 4, dims, str, box, 2)) return e;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)Cin, (uint64_t)9 * Cout};
+    uint64_t str[1] = {(uint64_t)Cin * 2};
+    uint32_t box[2] = {kBK, (uint32_t)g.BN};
+    if (int e = e4t_tmap_encode(&mB, w, 2, dims, str, box, 2)) return e;
+  }
+  return launch_gemm(mA, mB, g, stream);
+}
