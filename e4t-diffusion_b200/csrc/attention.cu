@@ -1,0 +1,732 @@
+// e4t_b200 — fused attention core softmax(Q Kᵀ / sqrt(dh)) V for the SD-v1.4 UNet, tcgen05 + TMA (sm_100a).
+// Reference call site: F.scaled_dot_product_attention in AttnProcessor2_0 (e4t/models/cross_attention.py:521-531),
+// equivalently get_attention_scores + bmm (cross_attention.py:222-251,313-315).  No mask, no dropout, non-causal.
+//
+// Layout: Q [B][N][H*dh], K/V [B][M][H*dh] (token-major, heads are dh-wide column slices; row/batch strides are
+// arguments so Q/K/V may alias one fused projection output).  dh % 8 == 0, dh <= 192.
+// Head slices are addressed with 4-D tensor maps (d, head, token, batch); the d-extent of the map is dh, so TMA
+// zero-fills the 64-wide smem chunk beyond dh (no padding in HBM).
+//
+// Forward, per CTA = one (128-query tile, head, batch):
+//   warp0  TMA producer: Q once, K_j / V_j ring
+//   warp1  MMA issuer  : S_j = Q·K_jᵀ into TMEM (double buffered), O += P_j·V_j (V_j as MN-major B operand)
+//   warps4-7 softmax   : one query row per thread (TMEM lane == row, no shuffles): online softmax, P_j -> smem
+//                        (SWIZZLE_128B, K-major A operand), lazy rescale of O in TMEM.
+// Backward is two kernels that recompute P from the saved log-sum-exp:
+//   dQ  kernel (CTA = query tile): S, dP = dO·Vᵀ, dS = P∘(dP − D)·scale, dQ += dS·K
+//   dKV kernel (CTA = key tile)  : Sᵀ = K·Qᵀ, dPᵀ = V·dOᵀ, dV += Pᵀ·dO, dK += dSᵀ·Q
+#include "common.cuh"
+
+static constexpr float kLog2e = 1.4426950408889634f;
+
+struct AttnArgs {
+  int B, H, N, M, dh;
+  int DC;        // 64-wide chunks of dh
+  int dpad;      // dh rounded up to 16 (MMA N of the output GEMMs)
+  int BKV;       // key/value block (fwd, dQ) or query block (dKV), multiple of 16
+  int nblk;      // number of blocks looped over
+  int kst;       // ring stages
+  float scale;   // dh^-0.5
+  // pointers / strides (elements)
+  bf16* O;  long long ldo, o_bs;
+  float* LSE;    // [B][H][N]
+  const float* Dv;  // [B][H][N] rowsum(dO∘O)
+  bf16* dQ; long long lddq, dq_bs;
+  bf16* dK; long long lddk, dk_bs;
+  bf16* dV; long long lddv, dv_bs;
+};
+
+__device__ __forceinline__ void mma_kmajor(uint32_t d_tmem, uint32_t sA, uint32_t a_chunk, uint32_t sB,
+                                           uint32_t b_chunk, int dh, int DC, uint32_t idesc) {
+  // D = A[128][dh] · B[N][dh]ᵀ, both K-major, dh split in 64-wide chunks
+  uint32_t acc = 0;
+  for (int c = 0; c < DC; ++c) {
+    const int rem = dh - 64 * c;
+    const int ks = rem >= 64 ? 4 : (rem + 15) / 16;
+    for (int k = 0; k < ks; ++k) {
+      umma_bf16(d_tmem, umma_desc(sA + c * a_chunk + k * 32, 16, 1024), umma_desc(sB + c * b_chunk + k * 32, 16, 1024),
+                idesc, acc);
+      acc = 1;
+    }
+  }
+}
+__device__ __forceinline__ void mma_pv(uint32_t d_tmem, uint32_t sP, uint32_t sV, uint32_t v_chunk, int kdim,
+                                       uint32_t idesc, uint32_t acc) {
+  // D[128][dpad] (+)= P[128][kdim] (K-major, 64-col chunks of 16 KiB) · V[kdim][dpad] (MN-major, 64-wide d chunks)
+  for (int ks = 0; ks < kdim / 16; ++ks) {
+    umma_bf16(d_tmem, umma_desc(sP + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
+              umma_desc(sV + ks * 2048, v_chunk, 1024), idesc, acc);
+    acc = 1;
+  }
+}
+
+// =============================================================================================
+// Forward
+// =============================================================================================
+__global__ void __launch_bounds__(256, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                const __grid_constant__ CUtensorMap mapV, const AttnArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int q_bytes = a.DC * 16384;
+  const int kv_tile = a.DC * a.BKV * 128;
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + q_bytes;
+  uint8_t* sV = sK + a.kst * kv_tile;
+  uint8_t* sP = sV + a.kst * kv_tile;  // 2 x 16 KiB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 32768);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;
+  uint64_t* k_empty = k_full + 2;
+  uint64_t* v_full = k_empty + 2;
+  uint64_t* v_empty = v_full + 2;
+  uint64_t* s_full = v_empty + 2;
+  uint64_t* p_ready = s_full + 2;
+  uint64_t* o_done = p_ready + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+    }
+    mbar_init(p_ready, 128);
+    mbar_init(o_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tS0 = tmem, tO = tmem + 256;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, (uint32_t)q_bytes);
+      for (int c = 0; c < a.DC; ++c) tma_load_4d(sQ + c * 16384, &mapQ, q_full, c * 64, h, q0, b);
+      for (int j = 0; j < a.nblk; ++j) {
+        const int st = j % a.kst;
+        const uint32_t ph = (uint32_t)((j / a.kst) & 1);
+        mbar_wait(&k_empty[st], ph ^ 1u);
+        mbar_expect_tx(&k_full[st], (uint32_t)kv_tile);
+        for (int c = 0; c < a.DC; ++c)
+          tma_load_4d(sK + st * kv_tile + c * a.BKV * 128, &mapK, &k_full[st], c * 64, h, j * a.BKV, b);
+        mbar_wait(&v_empty[st], ph ^ 1u);
+        mbar_expect_tx(&v_full[st], (uint32_t)kv_tile);
+        for (int c = 0; c < a.DC; ++c)
+          tma_load_4d(sV + st * kv_tile + c * a.BKV * 128, &mapV, &v_full[st], c * 64, h, j * a.BKV, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_bf16((uint32_t)a.BKV, false, false);
+      const uint32_t idesc_o = umma_idesc_bf16((uint32_t)a.dpad, false, true);
+      mbar_wait(q_full, 0);
+      tc_fence_after();
+      // S_0
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      mma_kmajor(tS0, smem_u32(sQ), 16384, smem_u32(sK), a.BKV * 128, a.dh, a.DC, idesc_s);
+      umma_commit(&k_empty[0]);
+      umma_commit(&s_full[0]);
+      for (int j = 0; j < a.nblk; ++j) {
+        if (j + 1 < a.nblk) {
+          const int jn = j + 1, st = jn % a.kst;
+          mbar_wait(&k_full[st], (uint32_t)((jn / a.kst) & 1));
+          tc_fence_after();
+          mma_kmajor(tS0 + (uint32_t)(jn & 1) * 128u, smem_u32(sQ), 16384, smem_u32(sK + st * kv_tile), a.BKV * 128,
+                     a.dh, a.DC, idesc_s);
+          umma_commit(&k_empty[st]);
+          umma_commit(&s_full[jn & 1]);
+        }
+        const int st = j % a.kst;
+        mbar_wait(p_ready, (uint32_t)(j & 1));
+        mbar_wait(&v_full[st], (uint32_t)((j / a.kst) & 1));
+        tc_fence_after();
+        mma_pv(tO, smem_u32(sP), smem_u32(sV + st * kv_tile), a.BKV * 128, a.BKV, idesc_o, j > 0 ? 1u : 0u);
+        umma_commit(&v_empty[st]);
+        umma_commit(o_done);
+      }
+    }
+  } else if (warp >= 4) {
+    const int ew = warp - 4;
+    const int row = ew * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(ew * 32) << 16;
+    const float sl2 = a.scale * kLog2e;
+    float m = -INFINITY, l = 0.f;
+    for (int j = 0; j < a.nblk; ++j) {
+      const uint32_t tS = tS0 + (uint32_t)(j & 1) * 128u + lane_base;
+      mbar_wait(&s_full[j & 1], (uint32_t)((j >> 1) & 1));
+      tc_fence_after();
+      const int kv0 = j * a.BKV;
+      // pass 1: row max
+      float mx = -INFINITY;
+      for (int c = 0; c < a.BKV; c += 16) {
+        uint32_t v[16];
+        __syncwarp();
+        tmem_ld16(tS + (uint32_t)c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (kv0 + c + i < a.M) mx = fmaxf(mx, __uint_as_float(v[i]));
+      }
+      const float m_new = fmaxf(m, mx);
+      const float alpha = exp2f((m - m_new) * sl2);  // m = -inf on the first block -> 0
+      // P buffer and O are free once PV_{j-1} retired
+      if (j > 0) {
+        mbar_wait(o_done, (uint32_t)((j - 1) & 1));
+        tc_fence_after();
+      }
+      // pass 2: P = exp2((s - m_new) * sl2) -> smem (bf16, swizzled K-major), row sum
+      float rs = 0.f;
+      const float mb = m_new * sl2;
+      for (int c = 0; c < a.BKV; c += 16) {
+        uint32_t v[16];
+        __syncwarp();
+        tmem_ld16(tS + (uint32_t)c, v);
+        tmem_ld_wait();
+        float p[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          p[i] = (kv0 + c + i < a.M) ? exp2f(__uint_as_float(v[i]) * sl2 - mb) : 0.f;
+        }
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          w[i] = pack_bf16(p[2 * i], p[2 * i + 1]);
+          // accumulate the ROUNDED probabilities so that l matches what the PV MMA sums
+          const float2 r = unpack_bf16(w[i]);
+          rs += r.x + r.y;
+        }
+        uint8_t* pc = sP + (c >> 6) * 16384;
+        const uint32_t c16 = (uint32_t)((c & 63) >> 3);
+        *reinterpret_cast<uint4*>(pc + sw128_off((uint32_t)row, c16)) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(pc + sw128_off((uint32_t)row, c16 + 1)) = make_uint4(w[4], w[5], w[6], w[7]);
+      }
+      l = l * alpha + rs;
+      m = m_new;
+      // lazy rescale of the O accumulator (warp-uniform branch: tcgen05.ld/st are warp-collective)
+      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
+        for (int c = 0; c < a.dpad; c += 16) {
+          uint32_t v[16];
+          tmem_ld16(tO + lane_base + (uint32_t)c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+          tmem_st16(tO + lane_base + (uint32_t)c, v);
+        }
+        tmem_st_wait();
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(p_ready);
+    }
+    // epilogue
+    mbar_wait(o_done, (uint32_t)((a.nblk - 1) & 1));
+    tc_fence_after();
+    const int n = q0 + row;
+    const float inv_l = 1.f / l;
+    for (int c = 0; c < a.dpad; c += 16) {
+      uint32_t v[16];
+      __syncwarp();
+      tmem_ld16(tO + lane_base + (uint32_t)c, v);
+      tmem_ld_wait();
+      if (n < a.N) {
+        bf16* o = a.O + (long long)b * a.o_bs + (long long)n * a.ldo + h * a.dh + c;
+#pragma unroll
+        for (int i = 0; i < 16; i += 8) {
+          if (c + i < a.dh) {
+            *reinterpret_cast<uint4*>(o + i) =
+                make_uint4(pack_bf16(__uint_as_float(v[i]) * inv_l, __uint_as_float(v[i + 1]) * inv_l),
+                           pack_bf16(__uint_as_float(v[i + 2]) * inv_l, __uint_as_float(v[i + 3]) * inv_l),
+                           pack_bf16(__uint_as_float(v[i + 4]) * inv_l, __uint_as_float(v[i + 5]) * inv_l),
+                           pack_bf16(__uint_as_float(v[i + 6]) * inv_l, __uint_as_float(v[i + 7]) * inv_l));
+          }
+        }
+      }
+    }
+    if (n < a.N) a.LSE[((long long)b * a.H + h) * a.N + n] = m * a.scale + logf(l);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// =============================================================================================
+// D = rowsum(dO ∘ O)  per (b, h, n); one warp per (b, n, h)
+// =============================================================================================
+__global__ void attn_delta_kernel(const bf16* __restrict__ O, const bf16* __restrict__ dO, float* __restrict__ Dv,
+                                  int B, int H, int N, int dh, long long ldo, long long o_bs, long long lddo,
+                                  long long do_bs) {
+  const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (wid >= (long long)B * N * H) return;
+  const int h = (int)(wid % H);
+  const int n = (int)((wid / H) % N);
+  const int b = (int)(wid / ((long long)H * N));
+  const bf16* o = O + b * o_bs + (long long)n * ldo + h * dh;
+  const bf16* d = dO + b * do_bs + (long long)n * lddo + h * dh;
+  float acc = 0.f;
+  for (int v = lane; v < dh / 8; v += 32) {
+    const uint4 a = *reinterpret_cast<const uint4*>(o + v * 8);
+    const uint4 c = *reinterpret_cast<const uint4*>(d + v * 8);
+    const uint32_t as[4] = {a.x, a.y, a.z, a.w}, cs[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 x = unpack_bf16(as[i]), y = unpack_bf16(cs[i]);
+      acc += x.x * y.x + x.y * y.y;
+    }
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) Dv[((long long)b * H + h) * N + n] = acc;
+}
+
+// =============================================================================================
+// dQ kernel: CTA = (128-query tile, head, batch); loops over key blocks.
+//   TMEM: S [0,128) | dP [128,256) | dQ [256, 256+dpad)
+// =============================================================================================
+__global__ void __launch_bounds__(256, 1)
+attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                   const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapdO,
+                   const AttnArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int q_bytes = a.DC * 16384;
+  const int kv_tile = a.DC * a.BKV * 128;
+  uint8_t* sQ = smem;
+  uint8_t* sdO = sQ + q_bytes;
+  uint8_t* sK = sdO + q_bytes;
+  uint8_t* sV = sK + kv_tile;
+  uint8_t* sdS = sV + kv_tile;  // 2 x 16 KiB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + 32768);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;
+  uint64_t* kv_empty = bars + 2;
+  uint64_t* sp_full = bars + 3;
+  uint64_t* ds_ready = bars + 4;
+  uint64_t* dq_done = bars + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    mbar_init(kv_full, 1);
+    mbar_init(kv_empty, 1);
+    mbar_init(sp_full, 1);
+    mbar_init(ds_ready, 128);
+    mbar_init(dq_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tS = tmem, tdP = tmem + 128, tdQ = tmem + 256;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, (uint32_t)(2 * q_bytes));
+      for (int c = 0; c < a.DC; ++c) {
+        tma_load_4d(sQ + c * 16384, &mapQ, q_full, c * 64, h, q0, b);
+        tma_load_4d(sdO + c * 16384, &mapdO, q_full, c * 64, h, q0, b);
+      }
+      for (int j = 0; j < a.nblk; ++j) {
+        mbar_wait(kv_empty, (uint32_t)((j & 1) ^ 1));
+        mbar_expect_tx(kv_full, (uint32_t)(2 * kv_tile));
+        for (int c = 0; c < a.DC; ++c) {
+          tma_load_4d(sK + c * a.BKV * 128, &mapK, kv_full, c * 64, h, j * a.BKV, b);
+          tma_load_4d(sV + c * a.BKV * 128, &mapV, kv_full, c * 64, h, j * a.BKV, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_bf16((uint32_t)a.BKV, false, false);
+      const uint32_t idesc_o = umma_idesc_bf16((uint32_t)a.dpad, false, true);
+      mbar_wait(q_full, 0);
+      for (int j = 0; j < a.nblk; ++j) {
+        mbar_wait(kv_full, (uint32_t)(j & 1));
+        tc_fence_after();
+        mma_kmajor(tS, smem_u32(sQ), 16384, smem_u32(sK), a.BKV * 128, a.dh, a.DC, idesc_s);
+        mma_kmajor(tdP, smem_u32(sdO), 16384, smem_u32(sV), a.BKV * 128, a.dh, a.DC, idesc_s);
+        umma_commit(sp_full);
+        mbar_wait(ds_ready, (uint32_t)(j & 1));
+        tc_fence_after();
+        mma_pv(tdQ, smem_u32(sdS), smem_u32(sK), a.BKV * 128, a.BKV, idesc_o, j > 0 ? 1u : 0u);
+        umma_commit(kv_empty);
+        umma_commit(dq_done);
+      }
+    }
+  } else if (warp >= 4) {
+    const int ew = warp - 4;
+    const int row = ew * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(ew * 32) << 16;
+    const int n = q0 + row;
+    const float sl2 = a.scale * kLog2e;
+    const long long sidx = ((long long)b * a.H + h) * a.N + n;
+    const float lse2 = (n < a.N) ? a.LSE[sidx] * kLog2e : 0.f;
+    const float dlt = (n < a.N) ? a.Dv[sidx] : 0.f;
+    for (int j = 0; j < a.nblk; ++j) {
+      mbar_wait(sp_full, (uint32_t)(j & 1));
+      tc_fence_after();
+      // sp_full(j) was committed after dQ-MMA(j-1) was issued, so the dS buffer is free here.
+      const int kv0 = j * a.BKV;
+      for (int c = 0; c < a.BKV; c += 16) {
+        uint32_t s[16], dp[16];
+        __syncwarp();
+        tmem_ld16(tS + lane_base + (uint32_t)c, s);
+        tmem_ld16(tdP + lane_base + (uint32_t)c, dp);
+        tmem_ld_wait();
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float d0 = 0.f, d1 = 0.f;
+          if (n < a.N) {
+            if (kv0 + c + 2 * i < a.M) {
+              const float p = exp2f(__uint_as_float(s[2 * i]) * sl2 - lse2);
+              d0 = p * (__uint_as_float(dp[2 * i]) - dlt) * a.scale;
+            }
+            if (kv0 + c + 2 * i + 1 < a.M) {
+              const float p = exp2f(__uint_as_float(s[2 * i + 1]) * sl2 - lse2);
+              d1 = p * (__uint_as_float(dp[2 * i + 1]) - dlt) * a.scale;
+            }
+          }
+          w[i] = pack_bf16(d0, d1);
+        }
+        uint8_t* pc = sdS + (c >> 6) * 16384;
+        const uint32_t c16 = (uint32_t)((c & 63) >> 3);
+        *reinterpret_cast<uint4*>(pc + sw128_off((uint32_t)row, c16)) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(pc + sw128_off((uint32_t)row, c16 + 1)) = make_uint4(w[4], w[5], w[6], w[7]);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(ds_ready);
+    }
+    mbar_wait(dq_done, (uint32_t)((a.nblk - 1) & 1));
+    tc_fence_after();
+    for (int c = 0; c < a.dpad; c += 16) {
+      uint32_t v[16];
+      __syncwarp();
+      tmem_ld16(tdQ + lane_base + (uint32_t)c, v);
+      tmem_ld_wait();
+      if (n < a.N) {
+        bf16* o = a.dQ + (long long)b * a.dq_bs + (long long)n * a.lddq + h * a.dh + c;
+#pragma unroll
+        for (int i = 0; i < 16; i += 8) {
+          if (c + i < a.dh) {
+            *reinterpret_cast<uint4*>(o + i) =
+                make_uint4(pack_bf16(__uint_as_float(v[i]), __uint_as_float(v[i + 1])),
+                           pack_bf16(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])),
+                           pack_bf16(__uint_as_float(v[i + 4]), __uint_as_float(v[i + 5])),
+                           pack_bf16(__uint_as_float(v[i + 6]), __uint_as_float(v[i + 7])));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// =============================================================================================
+// dK/dV kernel: CTA = (128-key tile, head, batch); loops over query blocks of BKV (=BQ) rows.
+//   TMEM: Sᵀ [0,BQ) | dPᵀ [W,W+BQ) | dV [2W,2W+dpad) | dK [2W+dpad, 2W+2*dpad)   (W = BQ_max = 64 when dpad>128 else 128)
+// =============================================================================================
+__global__ void __launch_bounds__(256, 1)
+attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                    const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapdO,
+                    const AttnArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int BQ = a.BKV;
+  const int kv_bytes = a.DC * 16384;
+  const int q_tile = a.DC * BQ * 128;
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + kv_bytes;
+  uint8_t* sQ = sV + kv_bytes;
+  uint8_t* sdO = sQ + q_tile;
+  uint8_t* sPT = sdO + q_tile;   // 2 x 16 KiB
+  uint8_t* sdST = sPT + 32768;   // 2 x 16 KiB
+  float* sLSE = reinterpret_cast<float*>(sdST + 32768);  // [128]
+  float* sD = sLSE + 128;                                // [128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sD + 128);
+  uint64_t* kv_full = bars;
+  uint64_t* q_full = bars + 1;
+  uint64_t* q_empty = bars + 2;
+  uint64_t* sp_full = bars + 3;
+  uint64_t* ds_ready = bars + 4;
+  uint64_t* acc_done = bars + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  if (warp == 1 && lane == 0) {
+    mbar_init(kv_full, 1);
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
+    mbar_init(sp_full, 1);
+    mbar_init(ds_ready, 128);
+    mbar_init(acc_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t sp_cols = a.dpad > 128 ? 64u : 128u;
+  const uint32_t tST = tmem, tdPT = tmem + sp_cols, tdV = tmem + 2 * sp_cols, tdK = tmem + 2 * sp_cols + (uint32_t)a.dpad;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(kv_full, (uint32_t)(2 * kv_bytes));
+      for (int c = 0; c < a.DC; ++c) {
+        tma_load_4d(sK + c * 16384, &mapK, kv_full, c * 64, h, k0, b);
+        tma_load_4d(sV + c * 16384, &mapV, kv_full, c * 64, h, k0, b);
+      }
+      for (int j = 0; j < a.nblk; ++j) {
+        mbar_wait(q_empty, (uint32_t)((j & 1) ^ 1));
+        mbar_expect_tx(q_full, (uint32_t)(2 * q_tile));
+        for (int c = 0; c < a.DC; ++c) {
+          tma_load_4d(sQ + c * BQ * 128, &mapQ, q_full, c * 64, h, j * BQ, b);
+          tma_load_4d(sdO + c * BQ * 128, &mapdO, q_full, c * 64, h, j * BQ, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_bf16((uint32_t)BQ, false, false);
+      const uint32_t idesc_o = umma_idesc_bf16((uint32_t)a.dpad, false, true);
+      mbar_wait(kv_full, 0);
+      for (int j = 0; j < a.nblk; ++j) {
+        mbar_wait(q_full, (uint32_t)(j & 1));
+        tc_fence_after();
+        mma_kmajor(tST, smem_u32(sK), 16384, smem_u32(sQ), BQ * 128, a.dh, a.DC, idesc_s);
+        mma_kmajor(tdPT, smem_u32(sV), 16384, smem_u32(sdO), BQ * 128, a.dh, a.DC, idesc_s);
+        umma_commit(sp_full);
+        mbar_wait(ds_ready, (uint32_t)(j & 1));
+        tc_fence_after();
+        mma_pv(tdV, smem_u32(sPT), smem_u32(sdO), BQ * 128, BQ, idesc_o, j > 0 ? 1u : 0u);
+        mma_pv(tdK, smem_u32(sdST), smem_u32(sQ), BQ * 128, BQ, idesc_o, j > 0 ? 1u : 0u);
+        umma_commit(q_empty);
+        umma_commit(acc_done);
+      }
+    }
+  } else if (warp >= 4) {
+    const int ew = warp - 4;
+    const int row = ew * 32 + lane;  // key index within the tile
+    const uint32_t lane_base = (uint32_t)(ew * 32) << 16;
+    const int kv = k0 + row;
+    const bool kv_ok = kv < a.M;
+    const float sl2 = a.scale * kLog2e;
+    const long long sbase = ((long long)b * a.H + h) * a.N;
+    for (int j = 0; j < a.nblk; ++j) {
+      // stage LSE / D of this query block (previous block's readers are past the named barrier below)
+      const int qn = j * BQ + row;
+      if (row < BQ) {
+        sLSE[row] = (qn < a.N) ? a.LSE[sbase + qn] * kLog2e : 0.f;
+        sD[row] = (qn < a.N) ? a.Dv[sbase + qn] : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(sp_full, (uint32_t)(j & 1));
+      tc_fence_after();
+      for (int c = 0; c < BQ; c += 16) {
+        uint32_t s[16], dp[16];
+        __syncwarp();
+        tmem_ld16(tST + lane_base + (uint32_t)c, s);
+        tmem_ld16(tdPT + lane_base + (uint32_t)c, dp);
+        tmem_ld_wait();
+        uint32_t wp[8], wd[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float p0 = 0.f, p1 = 0.f, d0 = 0.f, d1 = 0.f;
+          const int q_a = j * BQ + c + 2 * i;
+          if (kv_ok && q_a < a.N) {
+            p0 = exp2f(__uint_as_float(s[2 * i]) * sl2 - sLSE[c + 2 * i]);
+            d0 = p0 * (__uint_as_float(dp[2 * i]) - sD[c + 2 * i]) * a.scale;
+          }
+          if (kv_ok && q_a + 1 < a.N) {
+            p1 = exp2f(__uint_as_float(s[2 * i + 1]) * sl2 - sLSE[c + 2 * i + 1]);
+            d1 = p1 * (__uint_as_float(dp[2 * i + 1]) - sD[c + 2 * i + 1]) * a.scale;
+          }
+          wp[i] = pack_bf16(p0, p1);
+          wd[i] = pack_bf16(d0, d1);
+        }
+        const uint32_t c16 = (uint32_t)((c & 63) >> 3);
+        uint8_t* pp = sPT + (c >> 6) * 16384;
+        uint8_t* pd = sdST + (c >> 6) * 16384;
+        *reinterpret_cast<uint4*>(pp + sw128_off((uint32_t)row, c16)) = make_uint4(wp[0], wp[1], wp[2], wp[3]);
+        *reinterpret_cast<uint4*>(pp + sw128_off((uint32_t)row, c16 + 1)) = make_uint4(wp[4], wp[5], wp[6], wp[7]);
+        *reinterpret_cast<uint4*>(pd + sw128_off((uint32_t)row, c16)) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+        *reinterpret_cast<uint4*>(pd + sw128_off((uint32_t)row, c16 + 1)) = make_uint4(wd[4], wd[5], wd[6], wd[7]);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(ds_ready);
+      // all 128 threads are done reading sLSE/sD for this block before the next block overwrites them
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+    }
+    mbar_wait(acc_done, (uint32_t)((a.nblk - 1) & 1));
+    tc_fence_after();
+    for (int which = 0; which < 2; ++which) {
+      const uint32_t tacc = which == 0 ? tdV : tdK;
+      bf16* base = which == 0 ? a.dV + (long long)b * a.dv_bs + (long long)kv * a.lddv
+                              : a.dK + (long long)b * a.dk_bs + (long long)kv * a.lddk;
+      for (int c = 0; c < a.dpad; c += 16) {
+        uint32_t v[16];
+        __syncwarp();
+        tmem_ld16(tacc + lane_base + (uint32_t)c, v);
+        tmem_ld_wait();
+        if (kv_ok) {
+          bf16* o = base + h * a.dh + c;
+#pragma unroll
+          for (int i = 0; i < 16; i += 8) {
+            if (c + i < a.dh) {
+              *reinterpret_cast<uint4*>(o + i) =
+                  make_uint4(pack_bf16(__uint_as_float(v[i]), __uint_as_float(v[i + 1])),
+                             pack_bf16(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])),
+                             pack_bf16(__uint_as_float(v[i + 4]), __uint_as_float(v[i + 5])),
+                             pack_bf16(__uint_as_float(v[i + 6]), __uint_as_float(v[i + 7])));
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// =============================================================================================
+// Host
+// =============================================================================================
+static int make_head_map(CUtensorMap* m, const void* p, int dh, int H, int rows, int B, long long ld, long long bs,
+                         int box_rows) {
+  uint64_t dims[4] = {(uint64_t)dh, (uint64_t)H, (uint64_t)rows, (uint64_t)B};
+  uint64_t str[3] = {(uint64_t)dh * 2, (uint64_t)ld * 2, (uint64_t)(B > 1 ? bs : (long long)rows * ld) * 2};
+  uint32_t box[4] = {64, 1, (uint32_t)box_rows, 1};
+  return e4t_tmap_encode(m, p, 4, dims, str, box, 2);
+}
+static int round16(int x) { return (x + 15) / 16 * 16; }
+
+static int attn_common_checks(int dh, long long ldq, long long ldk, long long ldv) {
+  E4T_CHECK(dh % 8 == 0 && dh >= 8 && dh <= 192, "attention: head dim %d unsupported (need dh %% 8 == 0, <= 192)", dh);
+  E4T_CHECK(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0, "attention: row strides must be multiples of 8 elements");
+  return 0;
+}
+
+extern "C" int e4t_attn_fwd(const void* Q, const void* K, const void* V, void* O, float* LSE, int B, int H, int N,
+                            int M, int dh, long long ldq, long long q_bs, long long ldk, long long k_bs,
+                            long long ldv, long long v_bs, long long ldo, long long o_bs, float scale,
+                            void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (int e = attn_common_checks(dh, ldq, ldk, ldv)) return e;
+  AttnArgs a;
+  memset(&a, 0, sizeof(a));
+  a.B = B; a.H = H; a.N = N; a.M = M; a.dh = dh;
+  a.DC = cdiv(dh, 64);
+  a.dpad = round16(dh);
+  a.BKV = M >= 128 ? 128 : round16(M);
+  a.nblk = cdiv(M, a.BKV);
+  a.kst = a.DC >= 3 ? 1 : 2;
+  a.scale = scale;
+  a.O = (bf16*)O; a.ldo = ldo; a.o_bs = o_bs; a.LSE = LSE;
+  CUtensorMap mQ, mK, mV;
+  if (int e = make_head_map(&mQ, Q, dh, H, N, B, ldq, q_bs, 128)) return e;
+  if (int e = make_head_map(&mK, K, dh, H, M, B, ldk, k_bs, a.BKV)) return e;
+  if (int e = make_head_map(&mV, V, dh, H, M, B, ldv, v_bs, a.BKV)) return e;
+  const size_t smem = (size_t)a.DC * 16384 + (size_t)2 * a.kst * a.DC * a.BKV * 128 + 32768 + 256 + 1024;
+  static bool attr = false;
+  if (!attr) {
+    E4T_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr = true;
+  }
+  E4T_CHECK(smem <= 227 * 1024, "e4t_attn_fwd: smem budget exceeded (%zu)", smem);
+  attn_fwd_kernel<<<dim3(cdiv(N, 128), H, B), 256, smem, st>>>(mQ, mK, mV, a);
+  E4T_COUNT_LAUNCH();
+  E4T_LAUNCH_CHECK();
+  return 0;
+}
+
+// Dv: fp32 scratch [B][H][N].
+extern "C" int e4t_attn_bwd(const void* Q, const void* K, const void* V, const void* O, const void* dO,
+                            const float* LSE, float* Dv, void* dQ, void* dK, void* dV, int B, int H, int N, int M,
+                            int dh, long long ldq, long long q_bs, long long ldk, long long k_bs, long long ldv,
+                            long long v_bs, long long ldo, long long o_bs, long long lddo, long long do_bs,
+                            long long lddq, long long dq_bs, long long lddk, long long dk_bs, long long lddv,
+                            long long dv_bs, float scale, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (int e = attn_common_checks(dh, ldq, ldk, ldv)) return e;
+  E4T_CHECK(lddo % 8 == 0 && lddq % 8 == 0 && lddk % 8 == 0 && lddv % 8 == 0, "e4t_attn_bwd: strides %% 8");
+  attn_delta_kernel<<<cdiv((long long)B * N * H, 8), 256, 0, st>>>((const bf16*)O, (const bf16*)dO, Dv, B, H, N, dh, ldo,
+                                                                   o_bs, lddo, do_bs);
+  E4T_COUNT_LAUNCH();
+  E4T_LAUNCH_CHECK();
+  static bool attr = false;
+  if (!attr) {
+    E4T_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    E4T_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr = true;
+  }
+  AttnArgs a;
+  memset(&a, 0, sizeof(a));
+  a.B = B; a.H = H; a.N = N; a.M = M; a.dh = dh;
+  a.DC = cdiv(dh, 64);
+  a.dpad = round16(dh);
+  a.scale = scale;
+  a.LSE = const_cast<float*>(LSE); a.Dv = Dv;
+  a.dQ = (bf16*)dQ; a.lddq = lddq; a.dq_bs = dq_bs;
+  a.dK = (bf16*)dK; a.lddk = lddk; a.dk_bs = dk_bs;
+  a.dV = (bf16*)dV; a.lddv = lddv; a.dv_bs = dv_bs;
+  {  // dQ
+    a.BKV = M >= 128 ? 128 : round16(M);
+    a.nblk = cdiv(M, a.BKV);
+    CUtensorMap mQ, mK, mV, mdO;
+    if (int e = make_head_map(&mQ, Q, dh, H, N, B, ldq, q_bs, 128)) return e;
+    if (int e = make_head_map(&mdO, dO, dh, H, N, B, lddo, do_bs, 128)) return e;
+    if (int e = make_head_map(&mK, K, dh, H, M, B, ldk, k_bs, a.BKV)) return e;
+    if (int e = make_head_map(&mV, V, dh, H, M, B, ldv, v_bs, a.BKV)) return e;
+    const size_t smem = (size_t)2 * a.DC * 16384 + (size_t)2 * a.DC * a.BKV * 128 + 32768 + 256 + 1024;
+    E4T_CHECK(smem <= 227 * 1024, "e4t_attn_bwd(dQ): smem budget exceeded (%zu)", smem);
+    attn_bwd_dq_kernel<<<dim3(cdiv(N, 128), H, B), 256, smem, st>>>(mQ, mK, mV, mdO, a);
+    E4T_COUNT_LAUNCH();
+    E4T_LAUNCH_CHECK();
+  }
+  {  // dK, dV
+    const int bq_max = a.dpad > 128 ? 64 : 128;
+    a.BKV = N >= bq_max ? bq_max : round16(N);
+    a.nblk = cdiv(N, a.BKV);
+    CUtensorMap mQ, mK, mV, mdO;
+    if (int e = make_head_map(&mQ, Q, dh, H, N, B, ldq, q_bs, a.BKV)) return e;
+    if (int e = make_head_map(&mdO, dO, dh, H, N, B, lddo, do_bs, a.BKV)) return e;
+    if (int e = make_head_map(&mK, K, dh, H, M, B, ldk, k_bs, 128)) return e;
+    if (int e = make_head_map(&mV, V, dh, H, M, B, ldv, v_bs, 128)) return e;
+    const size_t smem = (size_t)2 * a.DC * 16384 + (size_t)2 * a.DC * a.BKV * 128 + 65536 + 1024 + 256 + 1024;
+    E4T_CHECK(smem <= 227 * 1024, "e4t_attn_bwd(dKV): smem budget exceeded (%zu)", smem);
+    attn_bwd_dkv_kernel<<<dim3(cdiv(M, 128), H, B), 256, smem, st>>>(mQ, mK, mV, mdO, a);
+    E4T_COUNT_LAUNCH();
+    E4T_LAUNCH_CHECK();
+  }
+  return 0;
+}

@@ -84,3 +84,220 @@ def conv3x3(x, w9, *, bias=None, rowgroup=None, residual=None, out_dtype=BF16, f
               c_int(0 if out_dtype == BF16 else 1), ptr(bias), ptr(rowgroup), ptr(residual), c_int(force_bn),
               stream())
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# normalisation
+# ----------------------------------------------------------------------------------------------
+def groupnorm_fwd(x, gamma, beta, groups, eps, silu):
+    """x: (B,HW,C) or (B,H,W,C) bf16 NHWC.  Returns (y, stats[B,G,2] = (sum, sumsq))."""
+    assert x.dtype == BF16 and x.is_contiguous()
+    Bn, C = x.shape[0], x.shape[-1]
+    HW = x.numel() // (Bn * C)
+    y = torch.empty_like(x)
+    stats = torch.empty((Bn, groups, 2), device=x.device, dtype=F32)
+    _lib.call("e4t_groupnorm_fwd", ptr(x), ptr(gamma), ptr(beta), ptr(y), ptr(stats), c_int(Bn), c_int(HW), c_int(C),
+              c_int(groups), c_float(eps), c_int(int(silu)), stream())
+    return y, stats
+
+
+def groupnorm_bwd(x, dy, gamma, beta, stats, groups, eps, silu):
+    assert x.dtype == BF16 and dy.dtype == BF16 and x.is_contiguous() and dy.is_contiguous()
+    Bn, C = x.shape[0], x.shape[-1]
+    HW = x.numel() // (Bn * C)
+    dx = torch.empty_like(x)
+    scratch = torch.empty((Bn, groups, 2), device=x.device, dtype=F32)
+    _lib.call("e4t_groupnorm_bwd", ptr(x), ptr(dy), ptr(gamma), ptr(beta), ptr(stats), ptr(dx), ptr(scratch),
+              c_int(Bn), c_int(HW), c_int(C), c_int(groups), c_float(eps), c_int(int(silu)), stream())
+    return dx
+
+
+def layernorm_fwd(x, gamma, beta, eps):
+    assert x.dtype == BF16 and x.is_contiguous()
+    C = x.shape[-1]
+    rows = x.numel() // C
+    y = torch.empty_like(x)
+    stats = torch.empty((rows, 2), device=x.device, dtype=F32)
+    _lib.call("e4t_layernorm_fwd", ptr(x), ptr(gamma), ptr(beta), ptr(y), ptr(stats), c_ll(rows), c_int(C),
+              c_float(eps), stream())
+    return y, stats
+
+
+def layernorm_bwd(x, dy, gamma, stats, eps):
+    assert x.dtype == BF16 and dy.dtype == BF16 and x.is_contiguous() and dy.is_contiguous()
+    C = x.shape[-1]
+    rows = x.numel() // C
+    dx = torch.empty_like(x)
+    _lib.call("e4t_layernorm_bwd", ptr(x), ptr(dy), ptr(gamma), ptr(stats), ptr(dx), c_ll(rows), c_int(C),
+              c_float(eps), stream())
+    return dx
+
+
+# ----------------------------------------------------------------------------------------------
+# elementwise
+# ----------------------------------------------------------------------------------------------
+def geglu_fwd(h):
+    assert h.dtype == BF16 and h.is_contiguous()
+    F = h.shape[-1] // 2
+    rows = h.numel() // (2 * F)
+    out = torch.empty(h.shape[:-1] + (F,), device=h.device, dtype=BF16)
+    _lib.call("e4t_geglu_fwd", ptr(h), ptr(out), c_ll(rows), c_int(F), stream())
+    return out
+
+
+def geglu_bwd(h, dout):
+    assert h.dtype == BF16 and dout.dtype == BF16 and h.is_contiguous() and dout.is_contiguous()
+    F = h.shape[-1] // 2
+    rows = h.numel() // (2 * F)
+    dh = torch.empty_like(h)
+    _lib.call("e4t_geglu_bwd", ptr(h), ptr(dout), ptr(dh), c_ll(rows), c_int(F), stream())
+    return dh
+
+
+def resample2x(x, mode):
+    """NHWC bf16.  mode 0 nearest-up, 1 its adjoint, 2 stride-2 pick, 3 zero-insertion (adjoint of 2)."""
+    assert x.dtype == BF16 and x.is_contiguous() and x.dim() == 4
+    Bn, Hx, Wx, C = x.shape
+    if mode in (0, 3):
+        H, W = Hx, Wx
+        y = torch.empty((Bn, 2 * H, 2 * W, C), device=x.device, dtype=BF16)
+    else:
+        H, W = Hx // 2, Wx // 2
+        y = torch.empty((Bn, H, W, C), device=x.device, dtype=BF16)
+    _lib.call("e4t_resample2x", ptr(x), ptr(y), c_int(Bn), c_int(H), c_int(W), c_int(C), c_int(mode), stream())
+    return y
+
+
+def meanpool_fwd(x, out, c_off):
+    """x (B,HW,C)/(B,H,W,C) bf16 -> out[:, c_off:c_off+C] (fp32, (B, ldo))."""
+    assert x.dtype == BF16 and x.is_contiguous() and out.dtype == F32 and out.stride(1) == 1
+    Bn, C = x.shape[0], x.shape[-1]
+    HW = x.numel() // (Bn * C)
+    _lib.call("e4t_meanpool_fwd", ptr(x), ptr(out), c_int(Bn), c_int(HW), c_int(C), c_int(out.stride(0)), c_int(c_off),
+              stream())
+
+
+def meanpool_bwd(dout, shape, c_off):
+    assert dout.dtype == F32 and dout.stride(1) == 1
+    Bn, C = shape[0], shape[-1]
+    HW = 1
+    for s in shape[1:-1]:
+        HW *= s
+    dx = torch.empty(shape, device=dout.device, dtype=BF16)
+    _lib.call("e4t_meanpool_bwd", ptr(dout), ptr(dx), c_int(Bn), c_int(HW), c_int(C), c_int(dout.stride(0)),
+              c_int(c_off), stream())
+    return dx
+
+
+def conv_in_fwd(x, w, bias):
+    """x NCHW fp32 (B,Cin,H,W) -> NHWC bf16 (B,H,W,Cout).  w fp32 (Cout,Cin,3,3)."""
+    assert x.dtype == F32 and x.is_contiguous() and w.dtype == F32 and w.is_contiguous()
+    Bn, Cin, H, W = x.shape
+    Cout = w.shape[0]
+    y = torch.empty((Bn, H, W, Cout), device=x.device, dtype=BF16)
+    _lib.call("e4t_conv_in_fwd", ptr(x), ptr(w), ptr(bias), ptr(y), c_int(Bn), c_int(Cin), c_int(H), c_int(W),
+              c_int(Cout), stream())
+    return y
+
+
+def conv_out_fwd(x, w, bias):
+    """x NHWC bf16 (B,H,W,C) -> NCHW fp32 (B,Cout,H,W)."""
+    assert x.dtype == BF16 and x.is_contiguous() and w.dtype == F32 and w.is_contiguous()
+    Bn, H, W, C = x.shape
+    Cout = w.shape[0]
+    y = torch.empty((Bn, Cout, H, W), device=x.device, dtype=F32)
+    _lib.call("e4t_conv_out_fwd", ptr(x), ptr(w), ptr(bias), ptr(y), c_int(Bn), c_int(H), c_int(W), c_int(C),
+              c_int(Cout), stream())
+    return y
+
+
+def conv_out_bwd(dy, w, C):
+    assert dy.dtype == F32 and dy.is_contiguous()
+    Bn, Cout, H, W = dy.shape
+    dx = torch.empty((Bn, H, W, C), device=dy.device, dtype=BF16)
+    _lib.call("e4t_conv_out_bwd", ptr(dy), ptr(w), ptr(dx), c_int(Bn), c_int(H), c_int(W), c_int(C), c_int(Cout),
+              stream())
+    return dx
+
+
+# ----------------------------------------------------------------------------------------------
+# WeightOffsets
+# ----------------------------------------------------------------------------------------------
+def wo_factors(v, w1, b1, w2, b2, Wc, Wr):
+    R, C = Wc.shape[0], Wr.shape[0]
+    buf = torch.empty(2 * R + 3 * C, device=v.device, dtype=F32)
+    vx, a, vy, b, s = buf[:R], buf[R:2 * R], buf[2 * R:2 * R + C], buf[2 * R + C:2 * R + 2 * C], buf[2 * R + 2 * C:]
+    _lib.call("e4t_wo_factors_fwd", ptr(v), ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(Wc), ptr(Wr), ptr(vx), ptr(vy),
+              ptr(a), ptr(b), ptr(s), c_int(R), c_int(C), stream())
+    return vx, vy, a, b, s
+
+
+def wo_weff(W, a, bc, b, s, br):
+    C, R = W.shape
+    out = torch.empty((C, R), device=W.device, dtype=BF16)
+    _lib.call("e4t_wo_weff_fwd", ptr(W), ptr(a), ptr(bc), ptr(b), ptr(s), ptr(br), ptr(out), c_int(C), c_int(R),
+              stream())
+    return out
+
+
+def wo_bwd(dWeff, W, v, w1, w2, Wc, Wr, bc, vx, vy, a, b, s):
+    C, R = W.shape
+    dev = W.device
+    scratch = torch.empty(3 * C + 2 * R + R + C, device=dev, dtype=F32)
+    dv = torch.empty(1, device=dev, dtype=F32)
+    dw1 = torch.empty(R, device=dev, dtype=F32); db1 = torch.empty(R, device=dev, dtype=F32)
+    dw2 = torch.empty(C, device=dev, dtype=F32); db2 = torch.empty(C, device=dev, dtype=F32)
+    dWc = torch.empty((R, R), device=dev, dtype=F32); dbc = torch.empty(R, device=dev, dtype=F32)
+    dWr = torch.empty((C, C), device=dev, dtype=F32); dbr = torch.empty(C, device=dev, dtype=F32)
+    _lib.call("e4t_wo_bwd", ptr(dWeff), ptr(W), ptr(v), ptr(w1), ptr(w2), ptr(Wc), ptr(Wr), ptr(bc), ptr(vx), ptr(vy),
+              ptr(a), ptr(b), ptr(s), ptr(scratch), ptr(dv), ptr(dw1), ptr(db1), ptr(dw2), ptr(db2), ptr(dWc),
+              ptr(dbc), ptr(dWr), ptr(dbr), c_int(R), c_int(C), stream())
+    return dv, dw1, db1, dw2, db2, dWc, dbc, dWr, dbr
+
+
+def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0):
+    assert p.dtype == F32 and p.is_contiguous() and g.is_contiguous() and m.is_contiguous() and v.is_contiguous()
+    _lib.call("e4t_adamw_step", ptr(p), ptr(g), ptr(m), ptr(v), c_ll(p.numel()), c_float(lr), c_float(beta1),
+              c_float(beta2), c_float(eps), c_float(weight_decay), c_int(step), c_float(grad_scale), stream())
+
+
+# ----------------------------------------------------------------------------------------------
+# attention core
+# ----------------------------------------------------------------------------------------------
+def _bs(t):
+    return t.stride(0)
+
+
+def attn_fwd(q, k, v, heads, scale=None):
+    """q (B,N,H*dh), k/v (B,M,H*dh) bf16 (last dim contiguous; may be column slices of a fused projection).
+    Returns (o (B,N,H*dh) bf16, lse (B,H,N) fp32)."""
+    assert q.dtype == BF16 and k.dtype == BF16 and v.dtype == BF16
+    assert q.stride(-1) == 1 and k.stride(-1) == 1 and v.stride(-1) == 1
+    Bn, N, C = q.shape
+    M = k.shape[1]
+    dh = C // heads
+    scale = dh ** -0.5 if scale is None else scale
+    o = torch.empty((Bn, N, C), device=q.device, dtype=BF16)
+    lse = torch.empty((Bn, heads, N), device=q.device, dtype=F32)
+    _lib.call("e4t_attn_fwd", ptr(q), ptr(k), ptr(v), ptr(o), ptr(lse), c_int(Bn), c_int(heads), c_int(N), c_int(M),
+              c_int(dh), c_ll(q.stride(1)), c_ll(_bs(q)), c_ll(k.stride(1)), c_ll(_bs(k)), c_ll(v.stride(1)),
+              c_ll(_bs(v)), c_ll(o.stride(1)), c_ll(_bs(o)), c_float(scale), stream())
+    return o, lse
+
+
+def attn_bwd(q, k, v, o, do, lse, heads, scale=None):
+    assert do.dtype == BF16 and do.stride(-1) == 1
+    Bn, N, C = q.shape
+    M = k.shape[1]
+    dh = C // heads
+    scale = dh ** -0.5 if scale is None else scale
+    dq = torch.empty((Bn, N, C), device=q.device, dtype=BF16)
+    dk = torch.empty((Bn, M, C), device=q.device, dtype=BF16)
+    dv = torch.empty((Bn, M, C), device=q.device, dtype=BF16)
+    dlt = torch.empty((Bn, heads, N), device=q.device, dtype=F32)
+    _lib.call("e4t_attn_bwd", ptr(q), ptr(k), ptr(v), ptr(o), ptr(do), ptr(lse), ptr(dlt), ptr(dq), ptr(dk), ptr(dv),
+              c_int(Bn), c_int(heads), c_int(N), c_int(M), c_int(dh), c_ll(q.stride(1)), c_ll(_bs(q)),
+              c_ll(k.stride(1)), c_ll(_bs(k)), c_ll(v.stride(1)), c_ll(_bs(v)), c_ll(o.stride(1)), c_ll(_bs(o)),
+              c_ll(do.stride(1)), c_ll(_bs(do)), c_ll(dq.stride(1)), c_ll(_bs(dq)), c_ll(dk.stride(1)), c_ll(_bs(dk)),
+              c_ll(dv.stride(1)), c_ll(_bs(dv)), c_float(scale), stream())
+    return dq, dk, dv
