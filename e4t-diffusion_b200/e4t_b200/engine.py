@@ -1,0 +1,165 @@
+"""The E4T pre-training step (pretrain_e4t.py:595-654) assembled from the `e4t` module mirror, with the pieces the
+reference gets from accelerate/torch.optim rebuilt B200-first:
+
+  * FlatAdamW     — all trainable parameters (WeightOffsets + encoder) re-homed into ONE fp32 arena with a matching
+                    gradient arena; the optimiser is a single fused sm_100a kernel over the arena and the
+                    data-parallel gradient exchange is ONE NCCL all-reduce of the gradient arena
+                    (reference: DDP buckets over every requires_grad parameter, ≈4.9 GB; here 1.5 GB).
+  * PretrainStep  — the loop body given explicit (pixel_values, latents, noise, timesteps, input_ids).
+"""
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+from . import functional as FN
+from . import ops
+
+PLACEHOLDER_FALLBACK = 49408
+
+
+def ddpm_alphas_cumprod(n=1000, beta_start=0.00085, beta_end=0.012, device="cpu"):
+    """SD-v1.x DDPMScheduler (scaled_linear betas), as used by noise_scheduler.add_noise (pretrain_e4t.py:621)."""
+    betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, n, dtype=torch.float32, device=device) ** 2
+    return torch.cumprod(1.0 - betas, dim=0)
+
+
+def add_noise(latents, noise, timesteps, acp):
+    a = acp[timesteps] ** 0.5
+    s = (1 - acp[timesteps]) ** 0.5
+    return a.view(-1, 1, 1, 1) * latents + s.view(-1, 1, 1, 1) * noise
+
+
+class FlatAdamW:
+    """torch.optim.AdamW semantics over a flat arena (amsgrad=False).  `params`: iterable of nn.Parameter."""
+
+    def __init__(self, params, lr=1.6e-5, betas=(0.9, 0.999), weight_decay=1e-2, eps=1e-8, process_group=None):
+        seen, plist = set(), []
+        for p in params:
+            if p.requires_grad and id(p) not in seen:
+                seen.add(id(p))
+                plist.append(p)
+        assert plist, "no trainable parameters"
+        dev = plist[0].device
+        assert dev.type == "cuda", "FlatAdamW runs the fused sm_100a kernel: parameters must be on a CUDA device"
+        self.params = plist
+        self.lr, self.betas, self.weight_decay, self.eps = lr, betas, weight_decay, eps
+        self.process_group = process_group
+        # storages shared by several parameters (E4TEncoder's stacked first_linears) must stay contiguous: group by
+        # untyped storage and move each storage once
+        groups = {}
+        for p in plist:
+            groups.setdefault(p.untyped_storage().data_ptr(), []).append(p)
+        total = 0
+        layout = []
+        for sp, ps in groups.items():
+            base = min(p.data_ptr() for p in ps)
+            end = max(p.data_ptr() + p.numel() * 4 for p in ps)
+            n = (end - base) // 4
+            n_pad = (n + 3) // 4 * 4
+            layout.append((ps, base, n, total))
+            total += n_pad
+        self.numel = total
+        self.arena = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.grad = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.exp_avg = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.exp_avg_sq = torch.zeros(total, device=dev, dtype=torch.float32)
+        with torch.no_grad():
+            for ps, base, n, off in layout:
+                for p in ps:
+                    assert p.dtype == torch.float32 and p.is_contiguous()
+                    o = off + (p.data_ptr() - base) // 4
+                    self.arena[o:o + p.numel()].copy_(p.detach().reshape(-1))
+                for p in ps:
+                    o = off + (p.data_ptr() - base) // 4
+                    p.data = self.arena[o:o + p.numel()].view(p.shape)
+                    p.grad = self.grad[o:o + p.numel()].view(p.shape)
+        self.step_count = 0
+        FN.bump_param_epoch()
+        # modules that cache views of re-homed storages refresh themselves lazily (E4TEncoder._stacked)
+
+    def zero_grad(self, set_to_none=False):
+        self.grad.zero_()
+
+    def all_reduce_grads(self):
+        """Data-parallel gradient exchange: one NCCL all-reduce (SUM) of the gradient arena; the 1/world average
+        is folded into the optimiser kernel's grad_scale."""
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.process_group) > 1:
+            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.process_group)
+            return 1.0 / dist.get_world_size(self.process_group)
+        return 1.0
+
+    def step(self, grad_scale=1.0):
+        self.step_count += 1
+        ops.adamw_step(self.arena, self.grad, self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0], self.betas[1],
+                       self.eps, self.weight_decay, self.step_count, grad_scale)
+        FN.bump_param_epoch()
+
+
+def trainable_parameters(unet, e4t_encoder):
+    """optim_params of pretrain_e4t.py:274-278: encoder params with requires_grad + UNet params whose name has 'wo'."""
+    ps = [p for p in e4t_encoder.parameters() if p.requires_grad]
+    for n, p in unet.named_parameters():
+        if "wo" in n:
+            p.requires_grad = True
+            ps.append(p)
+    return ps
+
+
+class PretrainStep:
+    """One optimisation step == pretrain_e4t.py:595-654 on explicit inputs."""
+
+    def __init__(self, unet, e4t_encoder, text_encoder, placeholder_token_id, class_token_id, lr=1.6e-5,
+                 betas=(0.9, 0.999), weight_decay=1e-2, eps=1e-8, domain_embed_scale=0.1, reg_lambda=0.01,
+                 bos_id=49406, eos_id=49407, weight_dtype=torch.bfloat16, optimizer=True):
+        self.unet, self.enc, self.text = unet, e4t_encoder, text_encoder
+        self.placeholder_token_id = placeholder_token_id
+        self.domain_embed_scale, self.reg_lambda = domain_embed_scale, reg_lambda
+        self.weight_dtype = weight_dtype
+        dev = unet.device
+        self.acp = ddpm_alphas_cumprod(device=dev)
+        self.text.requires_grad_(False)                                                  # pretrain_e4t.py:262-263
+        emb = self.text.get_input_embeddings()
+        with torch.no_grad():
+            self.class_embed = emb(torch.tensor([class_token_id], device=dev)).float()   # :561-564  (1,768)
+            ids = torch.tensor([[bos_id] + [eos_id] * 76], device=dev)
+            self.ehs_e4t = self.text(input_ids=ids)[0].to(weight_dtype)                  # :565-583  (1,77,768)
+        self.opt = FlatAdamW(trainable_parameters(unet, e4t_encoder), lr=lr, betas=betas, weight_decay=weight_decay,
+                             eps=eps) if optimizer else None
+
+    def placeholder_idxs(self, input_ids):
+        """[ids.index(placeholder_id) for ids in input_ids] (pretrain_e4t.py:617) — exact integer bookkeeping."""
+        return [row.index(self.placeholder_token_id) for row in input_ids.cpu().tolist()]
+
+    def forward_loss(self, batch):
+        pixel_values, latents, noise = batch["pixel_values"], batch["latents"], batch["noise"]
+        timesteps, input_ids = batch["timesteps"], batch["input_ids"]
+        B = latents.shape[0]
+        emb = self.text.get_input_embeddings()
+        with torch.no_grad():
+            inputs_embeds = emb(input_ids)                                               # :616
+        idxs = batch.get("placeholder_idxs")
+        if idxs is None:
+            idxs = self.placeholder_idxs(input_ids)                                      # :617
+        noisy = add_noise(latents, noise, timesteps, self.acp)                           # :621
+        enc = self.unet(noisy, timesteps, self.ehs_e4t.expand(B, -1, -1), return_encoder_outputs=True)   # :624
+        domain_embed = self.enc(x=pixel_values, unet_down_block_samples=enc["down_block_samples"])       # :626
+        domain_embed = self.class_embed.clone().expand(B, -1) + self.domain_embed_scale * domain_embed.float()  # :628
+        # per-sample in-place row overwrite (:630-631) as one differentiable index_put
+        rows = torch.arange(B, device=latents.device)
+        cols = torch.as_tensor(idxs, device=latents.device)
+        inputs_embeds = inputs_embeds.to(domain_embed.dtype).index_put((rows, cols), domain_embed)
+        ehs = self.text(inputs_embeds=inputs_embeds.to(self.text.dtype))[0].to(self.weight_dtype)        # :634
+        pred = self.unet(noisy, timesteps, ehs).sample                                   # :636
+        loss_diff = F.mse_loss(pred.float(), noise.float(), reduction="mean")            # :645
+        loss_reg = self.reg_lambda * domain_embed.pow(2).sum()                           # :646
+        return dict(loss=loss_diff + loss_reg, loss_diff=loss_diff, loss_reg=loss_reg, pred=pred,
+                    domain_embed=domain_embed, placeholder_idxs=idxs)
+
+    def __call__(self, batch):
+        out = self.forward_loss(batch)
+        out["loss"].backward()                                                           # :648
+        if self.opt is not None:
+            scale = self.opt.all_reduce_grads()
+            self.opt.step(scale)                                                         # :652
+            self.opt.zero_grad()                                                         # :654
+        return out

@@ -1,0 +1,335 @@
+"""torch.autograd.Function adapters over the sm_100a kernels (e4t_b200.ops).
+
+Conventions on the device path
+  * activations: bf16, channels-last — images are (B,H,W,C) contiguous, tokens are (B,N,C) contiguous
+  * parameters: fp32 masters (nn.Parameter); kernels read bf16 operand copies made by `prepared()` and refreshed
+    whenever the master's version counter moves (optimizer step, load_state_dict)
+  * gradients: every Function returns dX; weight gradients are produced only for the E4T-trainable set
+    (WeightOffsets through W_eff, encoder head) — the base UNet weights are never updated by pretrain_e4t.py
+    (only `"wo"` and encoder params reach the optimizer, pretrain_e4t.py:274-278), so their grads are not computed.
+"""
+import torch
+
+from . import ops
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+PARAM_EPOCH = 0  # bumped by optimisers that update parameters behind torch's version counters (FlatAdamW)
+
+
+def bump_param_epoch():
+    global PARAM_EPOCH
+    PARAM_EPOCH += 1
+
+
+def prepared(param, key, fn):
+    """Cached derived tensor of a parameter (e.g. its bf16 / re-laid-out copy), refreshed on version change."""
+    cache = getattr(param, "_e4t_prep", None)
+    if cache is None:
+        cache = {}
+        try:
+            param._e4t_prep = cache
+        except Exception:
+            return fn(param.detach())
+    ent = cache.get(key)
+    ver = (param._version, param.data_ptr(), param.device, PARAM_EPOCH if param.requires_grad else 0)
+    if ent is None or ent[0] != ver:
+        with torch.no_grad():
+            ent = (ver, fn(param.detach()))
+        cache[key] = ent
+    return ent[1]
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def as_bf16(t):
+    return t if t.dtype == BF16 else t.to(BF16)
+
+
+# ----------------------------------------------------------------------------------------------
+# dense layers
+# ----------------------------------------------------------------------------------------------
+class LinearFn(torch.autograd.Function):
+    """y = x @ Wᵀ (+bias) (+residual).  W: bf16 (N,K) operand copy.  Backward: dX only (+ pass-through to residual)."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, residual):
+        shp = x.shape
+        x2 = _c(x).view(-1, shp[-1])
+        res2 = None if residual is None else _c(residual).view(-1, w.shape[0])
+        y = ops.gemm(x2, w, bias=bias, residual=res2)
+        ctx.save_for_backward(w)
+        ctx.shp = shp
+        ctx.has_res = residual is not None
+        return y.view(*shp[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        (w,) = ctx.saved_tensors
+        dy2 = _c(dy).view(-1, w.shape[0])
+        dx = ops.gemm(dy2, w, b_mn=True).view(ctx.shp) if ctx.needs_input_grad[0] else None
+        return dx, None, None, (dy if ctx.has_res else None)
+
+
+class WOLinearFn(torch.autograd.Function):
+    """y = x @ W_effᵀ where W_eff (bf16) is the WeightOffsets-modulated projection (cross_attention.py:506,516,518).
+    `carrier` is the fp32 (C,R) autograd handle produced next to W_eff by WOEffectiveFn: the weight gradient is
+    returned for it so that it stays fp32 while it is summed over the two UNet passes of a step.
+    Backward: dX and dW_eff (split-K tcgen05 GEMM over the token dim, fp32 atomics)."""
+
+    @staticmethod
+    def forward(ctx, x, w_eff, carrier):
+        shp = x.shape
+        x2 = _c(x).view(-1, shp[-1])
+        y = ops.gemm(x2, w_eff)
+        ctx.save_for_backward(x2, w_eff)
+        ctx.shp = shp
+        return y.view(*shp[:-1], w_eff.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w_eff = ctx.saved_tensors
+        C, R = w_eff.shape
+        dy2 = _c(dy).view(-1, C)
+        dx = ops.gemm(dy2, w_eff, b_mn=True).view(ctx.shp) if ctx.needs_input_grad[0] else None
+        dw = None
+        if ctx.needs_input_grad[2]:
+            m = x2.shape[0]
+            dw = torch.zeros((C, R), device=x2.device, dtype=F32)
+            tiles = ((C + 127) // 128) * ((R + 127) // 128)
+            splits = max(1, min((m + 63) // 64, (2 * 148 + tiles - 1) // tiles))
+            ops.gemm(dy2, x2, a_mn=True, b_mn=True, out=dw, accumulate=True, splits=splits)
+        return dx, None, dw
+
+
+class Conv3x3Fn(torch.autograd.Function):
+    """3x3/s1/p1 convolution on NHWC (+bias +per-image row add (time embedding) +residual).  Backward: dX via the same
+    implicit-GEMM kernel with the flipped/transposed taps; pass-through to residual."""
+
+    @staticmethod
+    def forward(ctx, x, w9, w9_dgrad, bias, rowgroup, residual):
+        y = ops.conv3x3(_c(x), w9, bias=bias, rowgroup=rowgroup, residual=None if residual is None else _c(residual))
+        ctx.save_for_backward(w9_dgrad)
+        ctx.has_res = residual is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (w9_dgrad,) = ctx.saved_tensors
+        dy = _c(dy)
+        dx = ops.conv3x3(dy, w9_dgrad) if ctx.needs_input_grad[0] else None
+        return dx, None, None, None, None, (dy if ctx.has_res else None)
+
+
+class ResampleFn(torch.autograd.Function):
+    """mode 0: nearest x2 upsample; mode 2: stride-2 pick.  Backward is the adjoint kernel (modes 1 / 3)."""
+
+    @staticmethod
+    def forward(ctx, x, mode):
+        ctx.mode = mode
+        return ops.resample2x(_c(x), mode)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.resample2x(_c(dy), 1 if ctx.mode == 0 else 3), None
+
+
+class ConvOutFn(torch.autograd.Function):
+    """UNet conv_out: NHWC bf16 -> NCHW fp32 (unet_2d_condition.py:557)."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias):
+        ctx.save_for_backward(w)
+        ctx.C = x.shape[-1]
+        return ops.conv_out_fwd(_c(x), w, bias)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (w,) = ctx.saved_tensors
+        return ops.conv_out_bwd(_c(dy.float()), w, ctx.C), None, None
+
+
+# ----------------------------------------------------------------------------------------------
+# normalisation / activation
+# ----------------------------------------------------------------------------------------------
+class GroupNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, groups, eps, silu):
+        x = _c(x)
+        y, stats = ops.groupnorm_fwd(x, gamma, beta, groups, eps, silu)
+        ctx.save_for_backward(x, gamma, beta, stats)
+        ctx.cfg = (groups, eps, silu)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, beta, stats = ctx.saved_tensors
+        groups, eps, silu = ctx.cfg
+        return ops.groupnorm_bwd(x, _c(dy), gamma, beta, stats, groups, eps, silu), None, None, None, None, None
+
+
+class LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        x = _c(x)
+        y, stats = ops.layernorm_fwd(x, gamma, beta, eps)
+        ctx.save_for_backward(x, gamma, stats)
+        ctx.eps = eps
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, stats = ctx.saved_tensors
+        return ops.layernorm_bwd(x, _c(dy), gamma, stats, ctx.eps), None, None, None
+
+
+class GEGLUFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h):
+        h = _c(h)
+        ctx.save_for_backward(h)
+        return ops.geglu_fwd(h)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (h,) = ctx.saved_tensors
+        return ops.geglu_bwd(h, _c(dout))
+
+
+# ----------------------------------------------------------------------------------------------
+# attention core
+# ----------------------------------------------------------------------------------------------
+class AttentionFn(torch.autograd.Function):
+    """softmax(QKᵀ/sqrt(dh))V on token-major tensors, taking the FUSED projection outputs so that the projection
+    backward sees one contiguous gradient:
+      self-attention : a = qkv (B,N,3C), b = None      -> grad (B,N,3C)
+      cross-attention: a = q (B,N,C),  b = kv (B,M,2C) -> grads (B,N,C), (B,M,2C)"""
+
+    @staticmethod
+    def forward(ctx, a, b, heads, scale):
+        a = _c(a)
+        if b is None:
+            C = a.shape[-1] // 3
+            q, k, v = a[..., :C], a[..., C:2 * C], a[..., 2 * C:]
+        else:
+            b = _c(b)
+            C = a.shape[-1]
+            q, k, v = a, b[..., :C], b[..., C:]
+        o, lse = ops.attn_fwd(q, k, v, heads, scale)
+        ctx.save_for_backward(a, b, o, lse)
+        ctx.cfg = (heads, scale)
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        a, b, o, lse = ctx.saved_tensors
+        heads, scale = ctx.cfg
+        if b is None:
+            C = a.shape[-1] // 3
+            q, k, v = a[..., :C], a[..., C:2 * C], a[..., 2 * C:]
+            da = torch.empty_like(a)
+            ops.attn_bwd(q, k, v, o, _c(do), lse, heads, scale, dq=da[..., :C], dk=da[..., C:2 * C], dv=da[..., 2 * C:])
+            return da, None, None, None
+        C = a.shape[-1]
+        q, k, v = a, b[..., :C], b[..., C:]
+        da = torch.empty_like(a)
+        db = torch.empty_like(b)
+        ops.attn_bwd(q, k, v, o, _c(do), lse, heads, scale, dq=da, dk=db[..., :C], dv=db[..., C:])
+        return da, db, None, None
+
+
+# ----------------------------------------------------------------------------------------------
+# WeightOffsets: fused effective projection weights of one attention module
+# ----------------------------------------------------------------------------------------------
+WO_EPOCH = 0  # bumped by every WOEffectiveFn.backward: cached W_eff graphs are single-use
+
+
+_WO_FIELDS = ("v", "linear1.weight", "linear1.bias", "linear2.weight", "linear2.bias", "linear_column.weight",
+              "linear_column.bias", "linear_row.weight", "linear_row.bias")
+
+
+class WOEffectiveFn(torch.autograd.Function):
+    """W_eff = W ⊙ (1 + Δ), Δ = b·aᵀ + s·b_cᵀ + b_r·1ᵀ (closed form of e4t/weightoffsets.py:14-23) for a GROUP of
+    projections that share their input (q,k,v of self-attention; k,v of cross-attention), written into one
+    row-concatenated bf16 matrix so that the projection is a single GEMM.
+
+    apply(n, W_1..W_n, (v,w1,β1,w2,β2,Wc,bc,Wr,br)_1..n) -> (W_eff (ΣC_i, R) bf16 [non-differentiable],
+                                                             carrier (ΣC_i, R) fp32 [uninitialised autograd handle]).
+    Backward: five mat-vec reductions of G = dW_eff ⊙ W per projection -> all nine WeightOffsets parameter grads
+    (SURVEY.md Appendix A); G is never materialised."""
+
+    @staticmethod
+    def forward(ctx, n, *args):
+        Ws = args[:n]
+        wo = [args[n + 9 * i:n + 9 * (i + 1)] for i in range(n)]
+        R = Ws[0].shape[1]
+        Ctot = sum(w.shape[0] for w in Ws)
+        out = torch.empty((Ctot, R), device=Ws[0].device, dtype=BF16)
+        saved = []
+        r0 = 0
+        for W, p in zip(Ws, wo):
+            v, w1, b1, w2, b2, Wc, bc, Wr, br = p
+            vx, vy, a, b, s = ops.wo_factors(v, w1, b1, w2, b2, Wc, Wr)
+            ops.wo_weff(W, a, bc, b, s, br, out=out[r0:r0 + W.shape[0]])
+            r0 += W.shape[0]
+            saved += [vx, vy, a, b, s]
+        ctx.n = n
+        ctx.save_for_backward(*args, *saved)
+        carrier = torch.empty((Ctot, R), device=out.device, dtype=F32)
+        ctx.mark_non_differentiable(out)
+        return out, carrier
+
+    @staticmethod
+    def backward(ctx, _unused, dW):
+        global WO_EPOCH
+        WO_EPOCH += 1
+        n = ctx.n
+        t = ctx.saved_tensors
+        Ws = t[:n]
+        wo = [t[n + 9 * i:n + 9 * (i + 1)] for i in range(n)]
+        fac = t[n + 9 * n:]
+        dW = _c(dW.float())
+        grads = []
+        r0 = 0
+        for i, (W, p) in enumerate(zip(Ws, wo)):
+            v, w1, b1, w2, b2, Wc, bc, Wr, br = p
+            vx, vy, a, b, s = fac[5 * i:5 * i + 5]
+            C = W.shape[0]
+            dv, dw1, db1, dw2, db2, dWc, dbc, dWr, dbr = ops.wo_bwd(dW[r0:r0 + C], W, v, w1, w2, Wc, Wr, bc, vx, vy, a,
+                                                                  b, s)
+            r0 += C
+            grads += [dv, dw1.view_as(w1), db1, dw2.view_as(w2), db2, dWc, dbc, dWr, dbr]
+        return (None,) + (None,) * n + tuple(grads)
+
+
+# ----------------------------------------------------------------------------------------------
+# E4T encoder feature pooling (encoder.py:147-148)
+# ----------------------------------------------------------------------------------------------
+class MeanPoolCatFn(torch.autograd.Function):
+    """cat_k mean_{HW}(map_k) -> (B, ΣC_k) fp32, maps are channels-last bf16 (B,H,W,C)."""
+
+    @staticmethod
+    def forward(ctx, *maps):
+        B = maps[0].shape[0]
+        total = sum(m.shape[-1] for m in maps)
+        out = torch.empty((B, total), device=maps[0].device, dtype=F32)
+        off = 0
+        for m in maps:
+            ops.meanpool_fwd(_c(m), out, off)
+            off += m.shape[-1]
+        ctx.shapes = [tuple(m.shape) for m in maps]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dout = _c(dout.float())
+        outs = []
+        off = 0
+        for i, shp in enumerate(ctx.shapes):
+            outs.append(ops.meanpool_bwd(dout, shp, off) if ctx.needs_input_grad[i] else None)
+            off += shp[-1]
+        return tuple(outs)

@@ -232,9 +232,11 @@ def wo_factors(v, w1, b1, w2, b2, Wc, Wr):
     return vx, vy, a, b, s
 
 
-def wo_weff(W, a, bc, b, s, br):
+def wo_weff(W, a, bc, b, s, br, out=None):
     C, R = W.shape
-    out = torch.empty((C, R), device=W.device, dtype=BF16)
+    if out is None:
+        out = torch.empty((C, R), device=W.device, dtype=BF16)
+    assert out.is_contiguous() and out.shape == (C, R) and out.dtype == BF16
     _lib.call("e4t_wo_weff_fwd", ptr(W), ptr(a), ptr(bc), ptr(b), ptr(s), ptr(br), ptr(out), c_int(C), c_int(R),
               stream())
     return out
@@ -285,15 +287,17 @@ def attn_fwd(q, k, v, heads, scale=None):
     return o, lse
 
 
-def attn_bwd(q, k, v, o, do, lse, heads, scale=None):
+def attn_bwd(q, k, v, o, do, lse, heads, scale=None, dq=None, dk=None, dv=None):
+    """dq/dk/dv may be preallocated (e.g. column slices of one fused (B,N,3C) gradient buffer)."""
     assert do.dtype == BF16 and do.stride(-1) == 1
     Bn, N, C = q.shape
     M = k.shape[1]
     dh = C // heads
     scale = dh ** -0.5 if scale is None else scale
-    dq = torch.empty((Bn, N, C), device=q.device, dtype=BF16)
-    dk = torch.empty((Bn, M, C), device=q.device, dtype=BF16)
-    dv = torch.empty((Bn, M, C), device=q.device, dtype=BF16)
+    dq = torch.empty((Bn, N, C), device=q.device, dtype=BF16) if dq is None else dq
+    dk = torch.empty((Bn, M, C), device=q.device, dtype=BF16) if dk is None else dk
+    dv = torch.empty((Bn, M, C), device=q.device, dtype=BF16) if dv is None else dv
+    assert dq.stride(-1) == 1 and dk.stride(-1) == 1 and dv.stride(-1) == 1
     dlt = torch.empty((Bn, heads, N), device=q.device, dtype=F32)
     _lib.call("e4t_attn_bwd", ptr(q), ptr(k), ptr(v), ptr(o), ptr(do), ptr(lse), ptr(dlt), ptr(dq), ptr(dk), ptr(dv),
               c_int(Bn), c_int(heads), c_int(N), c_int(M), c_int(dh), c_ll(q.stride(1)), c_ll(_bs(q)),

@@ -1,0 +1,115 @@
+/* e4t_b200.h — C-ABI of libe4t_b200.so: the sm_100a (B200) kernels behind the mkshing/e4t-diffusion module API.
+ *
+ * The reference has no FFI of its own (pure Python over ATen/cuBLAS/cuDNN/SDPA); these entry points are what its
+ * Python operator layer binds for the E4T pre-training hot path.  Each function cites the reference
+ * call it replaces.  Conventions:
+ *   - plain pointers + sizes only (no torch types); all pointers are DEVICE pointers unless stated otherwise
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous and stream-ordered, never allocates,
+ *     never synchronises, holds no state between calls (thread-safe by construction)
+ *   - returns 0 on success; non-zero -> e4t_last_error() describes the failure (the Python side raises)
+ *   - activations are bf16, channels-last: images [B][H][W][C], tokens [B][N][C]; parameters/statistics are fp32
+ */
+#ifndef E4T_B200_H
+#define E4T_B200_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- plumbing ---------------------------------------------------------------------------------------------- */
+const char* e4t_last_error(void);              /* message of the last failing call on this thread               */
+int e4t_version(void);                         /* 100 = 0.1.0                                                    */
+unsigned long long e4t_launch_count(void);     /* kernels launched by this library since the last reset          */
+void e4t_reset_launch_count(void);
+
+/* ---- tcgen05 GEMM engine ------------------------------------------------------------------------------------ */
+/* out[b] = alpha * op(A[b]) op(B[b])^T (+bias[n]) (+rowgroup[m / rows_per_group][n]) (+residual[m][n]).
+ * Replaces F.linear at e4t/models/cross_attention.py:506,516,518,534, attention.py:429 (GEGLU proj), the 1x1
+ * proj_in/proj_out convs of transformer_2d.py:153,209 and every autograd-generated dX / dW GEMM behind them.
+ * a_mn / b_mn = 0: operand stored [rows][K] (K contiguous); = 1: stored [K][rows] (rows contiguous).
+ * lda/ldb: row stride in elements (multiple of 8); a_bstride/b_bstride: batch stride, 0 = shared across the batch.
+ * out_mode 0: bf16 store, 1: fp32 store, 2: fp32 atomic accumulate (required when splits > 1: split-K).
+ * force_bn: N-tile override for tuning (0 = heuristic). */
+int e4t_gemm_bf16(const void* A, const void* B, void* out, int M, int N, int K, int batch, int a_mn, int b_mn,
+                  long long lda, long long ldb, long long a_bstride, long long b_bstride, int out_mode,
+                  long long ldo, long long out_bstride, const float* bias, const float* rowgroup,
+                  int rows_per_group, const void* residual, long long ldr, long long res_bstride, float alpha,
+                  int splits, int force_bn, void* stream);
+
+/* 3x3 / stride 1 / pad 1 convolution as implicit GEMM (9 taps x Cin/64 K-chunks, halo by TMA zero fill).
+ * Replaces nn.Conv2d inside diffusers ResnetBlock2D.conv1/conv2, Upsample2D.conv, Downsample2D.conv
+ * (constructed at e4t/models/unet_2d_blocks.py:481-492,760-771,801-808,1732-1743,1773-1774) and their dgrad.
+ * x [B][H][W][Cin] bf16 (Cin % 64 == 0, W | 128); w [9][Cout][Cin] bf16 (tap = ky*3+kx); out [B][H][W][Cout];
+ * bias fp32 [Cout]; rowgroup fp32 [B][Cout] (time-embedding projection added per image); residual bf16 like out. */
+int e4t_conv3x3_bf16(const void* x, const void* w, void* out, int B, int H, int W, int Cin, int Cout, int out_mode,
+                     const float* bias, const float* rowgroup, const void* residual, int force_bn, void* stream);
+
+/* ---- attention core ------------------------------------------------------------------------------------------ */
+/* O = softmax(Q K^T * scale) V, LSE = logsumexp rows.  Replaces F.scaled_dot_product_attention at
+ * e4t/models/cross_attention.py:527-529 (== get_attention_scores + bmm, :222-251,313-315).
+ * Q [B][N][H*dh], K/V [B][M][H*dh] with row strides ld* and batch strides *_bs (elements), dh % 8 == 0, <= 192.
+ * LSE fp32 [B][H][N]. */
+int e4t_attn_fwd(const void* Q, const void* K, const void* V, void* O, float* LSE, int B, int H, int N, int M, int dh,
+                 long long ldq, long long q_bs, long long ldk, long long k_bs, long long ldv, long long v_bs,
+                 long long ldo, long long o_bs, float scale, void* stream);
+/* Backward of the above (autograd of SDPA in the reference).  Dv: fp32 scratch [B][H][N]. */
+int e4t_attn_bwd(const void* Q, const void* K, const void* V, const void* O, const void* dO, const float* LSE,
+                 float* Dv, void* dQ, void* dK, void* dV, int B, int H, int N, int M, int dh, long long ldq,
+                 long long q_bs, long long ldk, long long k_bs, long long ldv, long long v_bs, long long ldo,
+                 long long o_bs, long long lddo, long long do_bs, long long lddq, long long dq_bs, long long lddk,
+                 long long dk_bs, long long lddv, long long dv_bs, float scale, void* stream);
+
+/* ---- normalisation ------------------------------------------------------------------------------------------- */
+/* GroupNorm (+ optional fused SiLU).  Replaces nn.GroupNorm + F.silu in diffusers ResnetBlock2D, Transformer2DModel
+ * .norm (transformer_2d.py:149,253) and conv_norm_out/conv_act (unet_2d_condition.py:554-556).
+ * x,y [B][HW][C] bf16; stats fp32 [B][G][2] = (sum, sum of squares), written by fwd and consumed by bwd. */
+int e4t_groupnorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* stats, int B, int HW,
+                      int C, int G, float eps, int act_silu, void* stream);
+int e4t_groupnorm_bwd(const void* x, const void* dy, const float* gamma, const float* beta, const float* stats,
+                      void* dx, float* scratch /* [B][G][2] */, int B, int HW, int C, int G, float eps, int act_silu,
+                      void* stream);
+/* LayerNorm over the last dim.  Replaces nn.LayerNorm at attention.py:258-273.  stats fp32 [rows][2] = (mean, rstd). */
+int e4t_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* stats, long long rows,
+                      int C, float eps, void* stream);
+int e4t_layernorm_bwd(const void* x, const void* dy, const float* gamma, const float* stats, void* dx, long long rows,
+                      int C, float eps, void* stream);
+
+/* ---- elementwise --------------------------------------------------------------------------------------------- */
+/* GEGLU: out = h[:, :F] * gelu(h[:, F:]) (attention.py:409-430). */
+int e4t_geglu_fwd(const void* h, void* out, long long rows, int F, void* stream);
+int e4t_geglu_bwd(const void* h, const void* dout, void* dh, long long rows, int F, void* stream);
+/* 2x spatial resampling on NHWC (H, W = the SMALL resolution): mode 0 nearest upsample (diffusers Upsample2D),
+ * 1 its adjoint, 2 stride-2 pick (Downsample2D = stride-1 conv sampled at even positions), 3 zero insertion. */
+int e4t_resample2x(const void* x, void* y, int B, int H, int W, int C, int mode, void* stream);
+/* UNet conv_in (unet_2d_condition.py:481): NCHW fp32 -> NHWC bf16; w fp32 [Cout][Cin][3][3]. */
+int e4t_conv_in_fwd(const float* x, const float* w, const float* bias, void* y, int B, int Cin, int H, int W,
+                    int Cout, void* stream);
+/* UNet conv_out (unet_2d_condition.py:557): NHWC bf16 -> NCHW fp32, and its input gradient. */
+int e4t_conv_out_fwd(const void* x, const float* w, const float* bias, float* y, int B, int H, int W, int C, int Cout,
+                     void* stream);
+int e4t_conv_out_bwd(const float* dy, const float* w, void* dx, int B, int H, int W, int C, int Cout, void* stream);
+/* E4TEncoder feature pooling (e4t/encoder.py:147-148): out[b][c_off + c] = mean over HW, and its adjoint. */
+int e4t_meanpool_fwd(const void* x, float* out, int B, int HW, int C, int ldo, int c_off, void* stream);
+int e4t_meanpool_bwd(const float* dout, void* dx, int B, int HW, int C, int ldo, int c_off, void* stream);
+
+/* ---- WeightOffsets (e4t/weightoffsets.py:14-23, applied at cross_attention.py:506,516,518) -------------------- */
+/* Closed form: vx = w1 v + b1, vy = w2 v + b2, a = Wc vx, b = Wr vy, s = Wr 1; Delta = b a^T + s bc^T + br 1^T. */
+int e4t_wo_factors_fwd(const float* v, const float* w1, const float* b1, const float* w2, const float* b2,
+                       const float* Wc, const float* Wr, float* vx, float* vy, float* a, float* b, float* s, int R,
+                       int C, void* stream);
+/* W_eff[c][r] = bf16(W[c][r] * (1 + Delta[c][r])) — `attn.to_q.weight * (1 + attn.wo_q())`. */
+int e4t_wo_weff_fwd(const float* W, const float* a, const float* bc, const float* b, const float* s, const float* br,
+                    void* w_eff, int C, int R, void* stream);
+/* All nine parameter gradients from the accumulated dW_eff (fp32 [C][R]); scratch fp32 [4C + 3R]. */
+int e4t_wo_bwd(const float* dWeff, const float* W, const float* v, const float* w1, const float* w2, const float* Wc,
+               const float* Wr, const float* bc, const float* vx, const float* vy, const float* a, const float* b,
+               const float* s, float* scratch, float* dv, float* dw1, float* db1, float* dw2, float* db2, float* dWc,
+               float* dbc, float* dWr, float* dbr, int R, int C, void* stream);
+
+/* ---- optimiser (torch.optim.AdamW at pretrain_e4t.py:389-392,652) ---------------------------------------------- */
+int e4t_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                   float eps, float weight_decay, int step, float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* E4T_B200_H */
