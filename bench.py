@@ -1,0 +1,417 @@
+#!/usr/bin/env python
+"""bench.py — E4T pre-training throughput on B200 (BASELINE.json metric: images/sec @512², per-GPU bs16, SD-v1.4).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch 16] [--impl ours|reference]
+
+One "step" = one pass of the hot path (pretrain_e4t.py:595-654: UNet encoder-half -> E4T encoder -> text encoder ->
+full UNet -> loss -> backward -> AdamW) over one batch of synthetic 512² inputs with random-init SD-v1.4 + ViT-H/14
+weights.  Prints ONE JSON line (rank 0).  `value` = device-resident throughput (inputs already in HBM), `e2e` = the
+same through the public API with pinned-host inputs copied every step and the loss read back every step.
+`--impl reference` times the CPU oracle (oracle/e4t_oracle.py, the restated reference path) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "e4t-diffusion_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+METRIC = "E4T pretrain images/sec @512^2 bs16 SD-v1.4"
+SD14 = dict(in_channels=4, out_channels=4, block_out_channels=(320, 640, 1280, 1280), layers_per_block=2,
+            attention_head_dim=8, cross_attention_dim=768, norm_num_groups=32, norm_eps=1e-5, sample_size=64)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=16, help="per-GPU batch (BASELINE config: 16)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-micro", action="store_true")
+    ap.add_argument("--profile-one-step", action="store_true", help="run W warm-up + 1 step and exit (for ncu)")
+    return ap.parse_args()
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(bf16_burst=d.get("bf16_tflops", 1590.0), bf16_sustained=d.get("bf16_tflops_sustained", 1400.0),
+                    hbm=d.get("hbm_gbs", 6650.0), source="measured (MEASURED_PEAKS.json)")
+    return dict(bf16_burst=1590.0, bf16_sustained=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# clocks sampling (nvidia-smi, DURING the timed region)
+# ------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# model / data
+# ------------------------------------------------------------------------------------------------------------------
+def build_models(device):
+    from e4t.encoder import E4TEncoder
+    from e4t.models.modeling_clip import CLIPTextConfig, CLIPTextModel
+    from e4t.models.unet_2d_condition import UNet2DConditionModel
+    torch.manual_seed(0)
+    with torch.device(device):
+        unet = UNet2DConditionModel(cross_attention_dim=768, sample_size=64)     # SD-v1.4 config (defaults + 768)
+        enc = E4TEncoder(word_embedding_dim=768, arch="ViT-H-14")
+        text = CLIPTextModel(CLIPTextConfig(vocab_size=49409))
+    text.to(torch.bfloat16)                                                      # pretrain_e4t.py:422-423
+    return unet, enc, text
+
+
+TEMPLATE_WORDS = [4, 4, 5, 5, 5, 6, 6, 6, 5, 6]   # placeholder index for the 10 templates (pretrain_e4t.py:36-47)
+
+
+def host_batch(B, seed, pinned=True):
+    """Synthetic per-step inputs on the host."""
+    import random
+    g = torch.Generator().manual_seed(seed)
+    rnd = random.Random(seed)
+    idxs = [TEMPLATE_WORDS[t] for t in rnd.choices(range(10), k=B)]
+    ids = torch.full((B, 77), 49407, dtype=torch.int64)
+    ids[:, 0] = 49406
+    for i, ix in enumerate(idxs):
+        ids[i, 1:ix] = torch.randint(300, 4000, (ix - 1,), generator=g)
+        ids[i, ix] = 49408
+    b = dict(pixel_values=torch.rand(B, 3, 512, 512, generator=g) * 2 - 1,
+             latents=torch.randn(B, 4, 64, 64, generator=g) * 0.18215, noise=torch.randn(B, 4, 64, 64, generator=g),
+             timesteps=torch.randint(0, 1000, (B,), generator=g, dtype=torch.int64), input_ids=ids,
+             placeholder_idxs=torch.tensor(idxs, dtype=torch.int64))
+    if pinned:
+        b = {k: v.pin_memory() for k, v in b.items()}
+    return b
+
+
+def to_device(b, device):
+    return {k: v.to(device, non_blocking=True) for k, v in b.items()}
+
+
+def batch_bytes(b):
+    return int(sum(v.numel() * v.element_size() for v in b.values()))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# micro-timing of the dominant kernels (CUDA events on the launching stream, L2 flushed between launches)
+# ------------------------------------------------------------------------------------------------------------------
+def micro_rooflines(B, peaks, device):
+    from e4t_b200 import ops
+    res = {}
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)   # > 126 MB L2
+
+    def timeit(fn, iters=8):
+        fn(); fn()
+        ts = []
+        for _ in range(iters):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        return ts[len(ts) // 2] * 1e-3
+
+    g = torch.Generator(device=device).manual_seed(1)
+    # (1) attention core, level-0 self-attention: N=M=4096, 8 heads x dh 40  (59% of attention FLOPs)
+    N, C, H = 4096, 320, 8
+    qkv = (torch.randn(B, N, 3 * C, device=device, generator=g) * 0.5).to(torch.bfloat16)
+    q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+    t = timeit(lambda: ops.attn_fwd(q, k, v, H))
+    fl = 4.0 * N * N * C * B
+    res["attn_fwd_L0_self"] = dict(ms=t * 1e3, tflops=fl / t / 1e12, flops=fl)
+    o, lse = ops.attn_fwd(q, k, v, H)
+    do = torch.randn_like(o)
+    t = timeit(lambda: ops.attn_bwd(q, k, v, o, do, lse, H))
+    res["attn_bwd_L0_self"] = dict(ms=t * 1e3, tflops=2.5 * fl / t / 1e12, flops=2.5 * fl,
+                                   note="algorithmic 2.5x fwd (recompute excluded)")
+    # (2) fused WO-modulated QKV projection GEMM, level 0: (B*4096, 320) x (960, 320)^T
+    x = (torch.randn(B * N, C, device=device, generator=g)).to(torch.bfloat16)
+    w = (torch.randn(3 * C, C, device=device, generator=g) * 0.05).to(torch.bfloat16)
+    t = timeit(lambda: ops.gemm(x, w))
+    fl2 = 2.0 * B * N * C * 3 * C
+    res["qkv_proj_L0"] = dict(ms=t * 1e3, tflops=fl2 / t / 1e12, flops=fl2)
+    # (3) GEGLU projection GEMM level 1 (B*1024, 640) x (5120, 640)^T and (4) 3x3 conv 320->320 @64x64
+    x1 = torch.randn(B * 1024, 640, device=device, generator=g).to(torch.bfloat16)
+    w1 = (torch.randn(5120, 640, device=device, generator=g) * 0.05).to(torch.bfloat16)
+    t = timeit(lambda: ops.gemm(x1, w1))
+    res["ff_proj_L1"] = dict(ms=t * 1e3, tflops=2.0 * B * 1024 * 640 * 5120 / t / 1e12)
+    xc = torch.randn(B, 64, 64, 320, device=device, generator=g).to(torch.bfloat16)
+    wc = (torch.randn(9, 320, 320, device=device, generator=g) * 0.05).to(torch.bfloat16)
+    t = timeit(lambda: ops.conv3x3(xc, wc))
+    res["conv3x3_320_64"] = dict(ms=t * 1e3, tflops=2.0 * B * 4096 * 9 * 320 * 320 / t / 1e12)
+    # (5) HBM-bound: GroupNorm+SiLU 320ch @64x64
+    gam = torch.ones(320, device=device); bet = torch.zeros(320, device=device)
+    t = timeit(lambda: ops.groupnorm_fwd(xc, gam, bet, 32, 1e-5, True))
+    byts = xc.numel() * 2 * 3  # stats read + apply read + write
+    res["groupnorm_silu_320_64"] = dict(ms=t * 1e3, gbs=byts / t / 1e9, frac_hbm=byts / t / 1e9 / peaks["hbm"])
+    del flush
+    return res
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU baseline (oracle port of the reference path) — bounded sample
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_oracle_setup():
+    from oracle import e4t_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    g = torch.Generator().manual_seed(0)
+
+    def rnd_sd(shapes):
+        sd = {}
+        for k, s in shapes.items():
+            if k.endswith(".v"):
+                sd[k] = torch.ones(1)
+            elif len(s) >= 2:
+                fan = 1
+                for d in s[1:]:
+                    fan *= d
+                sd[k] = torch.empty(s).uniform_(-1, 1, generator=g) / fan ** 0.5
+            elif k.endswith("weight"):
+                sd[k] = torch.ones(s)
+            else:
+                sd[k] = torch.zeros(s)
+        return sd
+
+    sd_u = rnd_sd(O.unet_param_shapes(O.SD14_UNET))
+    sd_e = rnd_sd(O.encoder_param_shapes(O.VIT_H14))
+    sd_t = rnd_sd(O.text_param_shapes(O.CLIP_TEXT_L))
+    train = [v for k, v in sd_u.items() if "wo" in k] + [v for k, v in sd_e.items() if not k.startswith("clip_vision.")]
+    for v in train:
+        v.requires_grad_(True)
+    opt = torch.optim.AdamW(train, lr=1.6e-5)
+    return O, sd_u, sd_e, sd_t, opt
+
+
+def cpu_oracle_step(state, B, seed):
+    O, sd_u, sd_e, sd_t, opt = state
+    batch = O.synth_batch(B, seed)
+    t0 = time.perf_counter()
+    out = O.pretrain_step(sd_u, O.SD14_UNET, sd_e, O.VIT_H14, sd_t, O.CLIP_TEXT_L, batch)
+    opt.zero_grad()
+    out["loss"].backward()
+    opt.step()
+    return time.perf_counter() - t0, float(out["loss"])
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port) on the host cores; rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    state = cpu_oracle_setup()
+    B = 1
+    t_w, _ = cpu_oracle_step(state, B, 1)                     # warm-up (also sizes the run)
+    budget = 200.0
+    steps = max(1, min(args.steps, int(budget // max(t_w, 1e-3))))
+    ts = []
+    for i in range(steps):
+        t, _ = cpu_oracle_step(state, B, 2 + i)
+        ts.append(t)
+    tot = sum(ts)
+    val = B * steps / tot
+    sample = (f"{steps} timed step(s) (of {args.steps} requested; capped to ~{int(budget)} s of CPU work) of the full "
+              f"pre-training step at B={B} image/step, SD-v1.4 UNet + ViT-H/14 + CLIP-L text, fp32, "
+              f"torch.set_num_threads({cores}); 1 warm-up step")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "images/sec", "n_gpus": args.gpus,
+            "steps": steps, "warmup": 1, "ms_per_step": tot / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "SD-v1.4 E4T pretrain step, random-init, 512^2 (CPU oracle port of the reference path)",
+                       "per_step_batch": B, "device": "host CPU"},
+            "cpu_baseline": {"value": val, "unit": "images/sec", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback "
+                         "(use --impl reference for the CPU oracle)")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    from e4t_b200 import _lib
+    from e4t_b200.engine import PretrainStep
+    _lib.load()
+    peaks = load_peaks()
+    B = args.batch
+
+    unet, enc, text = build_models(device)
+    step = PretrainStep(unet, enc, text, placeholder_token_id=49408, class_token_id=320, lr=1.6e-5,
+                        weight_dtype=torch.bfloat16)
+    n_train = step.opt.numel
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run_steps(n, batches, e2e):
+        """n steps; returns device time (s) via CUDA events and the last loss."""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        last = None
+        for i in range(n):
+            hb = batches[i % len(batches)]
+            b = to_device(hb, device) if e2e else hb
+            out = step(b)
+            if e2e:
+                last = out["loss"].item()          # device -> host read of the step result
+            else:
+                last = out["loss"]
+        e1.record()
+        barrier()
+        t = e0.elapsed_time(e1) * 1e-3
+        if world > 1:
+            tt = torch.tensor([t], device=device)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t = tt.item()
+        return t, (last if isinstance(last, float) else float(last))
+
+    host_batches = [host_batch(B, 42 + rank * 1000 + i) for i in range(4)]
+    dev_batches = [to_device(hb, device) for hb in host_batches]
+    h2d = batch_bytes(host_batches[0])
+
+    # warm-up (also builds the bf16 operand caches and first-call attributes)
+    run_steps(args.warmup, dev_batches, False)
+    if args.profile_one_step:
+        run_steps(1, dev_batches, False)
+        return
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    _lib.reset_launch_count()
+    t_dev, loss = run_steps(args.steps, dev_batches, False)
+    launches = _lib.launch_count()
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * args.steps / t_dev
+
+    e2e = None
+    if not args.no_e2e:
+        run_steps(1, host_batches, True)
+        t_e2e, _ = run_steps(args.steps, host_batches, True)
+        e2e = {"value": world * B * args.steps / t_e2e, "unit": "images/sec", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": 4, "ms_per_step": t_e2e / args.steps * 1e3}
+
+    micro, roof = None, None
+    if rank == 0 and not args.no_micro:
+        del dev_batches
+        torch.cuda.empty_cache()
+        micro = micro_rooflines(B, peaks, device)
+        a = micro["attn_fwd_L0_self"]
+        roof = {"kernel": "attn_fwd_kernel (level-0 self-attention core, N=M=4096, 8x40, B=%d)" % B,
+                "bound": "tensor", "achieved": a["tflops"], "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
+                "frac": a["tflops"] / peaks["bf16_burst"], "traffic": None,
+                "algorithmic_flops_per_launch": a["flops"], "peak_source": peaks["source"] + ", burst figure "
+                "(kernel timed alone, L2 flushed between launches)"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            state = cpu_oracle_setup()
+            t_cpu, _ = cpu_oracle_step(state, 1, 1)
+            cpu = {"value": 1.0 / t_cpu, "unit": "images/sec", "cores": os.cpu_count(), "kind": "port",
+                   "sample": "ONE full pre-training step at B=1 image (SD-v1.4 UNet x2 fwd + ViT-H/14 + CLIP-L text + "
+                             "bwd + AdamW), fp32 CPU oracle (oracle/e4t_oracle.py), all host threads, no warm-up"}
+            del state
+        except Exception as ex:  # the baseline must never take the GPU number down with it
+            cpu = {"value": None, "unit": "images/sec", "cores": os.cpu_count(), "kind": "port",
+                   "sample": f"failed: {type(ex).__name__}: {ex}"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": "SD-v1.4 E4T pretrain step (UNet enc-half + E4T encoder ViT-H/14 + CLIP text + "
+                                       "full UNet + loss + bwd + AdamW), random-init, 512^2 (64x64 latents)",
+                           "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                           "trainable_params": n_train,
+                           "l2": "inputs rotate over 4 batches; per-step working set (activations ~30 GB) >> 126 MB L2",
+                           "grad_allreduce": "one NCCL all-reduce of the flat fp32 grad arena" if world > 1 else "none"},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+                "gpu_launches_per_step": launches // max(args.steps, 1), "loss": loss, "roofline": roof, "kernels": micro,
+                "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
