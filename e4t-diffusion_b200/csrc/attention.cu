@@ -16,6 +16,7 @@
 //   dQ  kernel (CTA = query tile): S, dP = dO·Vᵀ, dS = P∘(dP − D)·scale, dQ += dS·K
 //   dKV kernel (CTA = key tile)  : Sᵀ = K·Qᵀ, dPᵀ = V·dOᵀ, dV += Pᵀ·dO, dK += dSᵀ·Q
 #include "common.cuh"
+#include <stdlib.h>
 
 static constexpr float kLog2e = 1.4426950408889634f;
 
@@ -62,10 +63,17 @@ __device__ __forceinline__ void mma_pv(uint32_t d_tmem, uint32_t sP, uint32_t sV
 
 // =============================================================================================
 // Forward
+//   softmax warps are organised as CG column groups x 4 lane quadrants: warp (4 + 4*g + e) owns TMEM lanes
+//   [32e, 32e+32) (the query rows) and the 16-column chunks c with (c/16) % CG == g of each S block, so that every
+//   SM sub-partition has CG resident softmax warps to overlap MUFU / FMA / TMEM latencies.  Row maxima are exchanged
+//   through shared memory (double buffered), row sums are combined once at the end.
 // =============================================================================================
-__global__ void __launch_bounds__(256, 1)
+template <int CG>
+__global__ void __launch_bounds__(128 + 128 * CG, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                 const __grid_constant__ CUtensorMap mapV, const AttnArgs a) {
+  constexpr int MAXC = 8 / CG;  // 16-column chunks per thread and block
+  constexpr int NSOFT = 128 * CG;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int q_bytes = a.DC * 16384;
@@ -74,7 +82,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
   uint8_t* sK = sQ + q_bytes;
   uint8_t* sV = sK + a.kst * kv_tile;
   uint8_t* sP = sV + a.kst * kv_tile;  // 2 x 16 KiB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 32768);
+  float* sMax = reinterpret_cast<float*>(sP + 32768);  // [2][CG][128]
+  float* sSum = sMax + 2 * CG * 128;                   // [CG][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sSum + CG * 128);
   uint64_t* q_full = bars;
   uint64_t* k_full = bars + 1;
   uint64_t* k_empty = k_full + 2;
@@ -97,7 +107,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
       mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
     }
-    mbar_init(p_ready, 128);
+    mbar_init(p_ready, NSOFT);
     mbar_init(o_done, 1);
     fence_mbar_init();
   }
@@ -131,7 +141,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
       const uint32_t idesc_o = umma_idesc_bf16((uint32_t)a.dpad, false, true);
       mbar_wait(q_full, 0);
       tc_fence_after();
-      // S_0
       mbar_wait(&k_full[0], 0);
       tc_fence_after();
       mma_kmajor(tS0, smem_u32(sQ), 16384, smem_u32(sK), a.BKV * 128, a.dh, a.DC, idesc_s);
@@ -157,71 +166,91 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
       }
     }
   } else if (warp >= 4) {
-    const int ew = warp - 4;
+    const int ew = (warp - 4) & 3;
+    const int cg = (warp - 4) >> 2;
     const int row = ew * 32 + lane;
     const uint32_t lane_base = (uint32_t)(ew * 32) << 16;
     const float sl2 = a.scale * kLog2e;
+    const int nchunk = a.BKV >> 4;
+    const int ochunk = a.dpad >> 4;
     float m = -INFINITY, l = 0.f;
     for (int j = 0; j < a.nblk; ++j) {
       const uint32_t tS = tS0 + (uint32_t)(j & 1) * 128u + lane_base;
       mbar_wait(&s_full[j & 1], (uint32_t)((j >> 1) & 1));
       tc_fence_after();
       const int kv0 = j * a.BKV;
-      // pass 1: row max
-      float mx = -INFINITY;
-      for (int c = 0; c < a.BKV; c += 16) {
-        uint32_t v[16];
-        __syncwarp();
-        tmem_ld16(tS + (uint32_t)c, v);
-        tmem_ld_wait();
+      // ---- load my column chunks of S (single TMEM pass) ----
+      uint32_t sv[MAXC][16];
+      __syncwarp();
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (kv0 + c + i < a.M) mx = fmaxf(mx, __uint_as_float(v[i]));
+      for (int i = 0; i < MAXC; ++i) {
+        const int ci = cg + i * CG;
+        if (ci < nchunk) tmem_ld16(tS + (uint32_t)(ci * 16), sv[i]);
       }
+      tmem_ld_wait();
+      const bool partial = kv0 + a.BKV > a.M;  // only the last block can be ragged
+      float mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < MAXC; ++i) {
+        const int ci = cg + i * CG;
+        if (ci < nchunk) {
+          if (!partial) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) mx = fmaxf(mx, __uint_as_float(sv[i][e]));
+          } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              if (kv0 + ci * 16 + e >= a.M) sv[i][e] = 0xff800000u;  // -inf
+              mx = fmaxf(mx, __uint_as_float(sv[i][e]));
+            }
+          }
+        }
+      }
+      // ---- exchange row maxima between the column groups ----
+      float* smx = sMax + (j & 1) * CG * 128;
+      smx[cg * 128 + row] = mx;
+      asm volatile("bar.sync 1, %0;" ::"n"(NSOFT) : "memory");
+#pragma unroll
+      for (int g = 0; g < CG; ++g) mx = fmaxf(mx, smx[g * 128 + row]);
       const float m_new = fmaxf(m, mx);
-      const float alpha = exp2f((m - m_new) * sl2);  // m = -inf on the first block -> 0
+      const float alpha = ex2_approx((m - m_new) * sl2);  // m = -inf on the first block -> 0
       // P buffer and O are free once PV_{j-1} retired
       if (j > 0) {
         mbar_wait(o_done, (uint32_t)((j - 1) & 1));
         tc_fence_after();
       }
-      // pass 2: P = exp2((s - m_new) * sl2) -> smem (bf16, swizzled K-major), row sum
+      // ---- P = exp2((s - m_new) * sl2) -> smem (bf16, swizzled K-major), partial row sum ----
       float rs = 0.f;
       const float mb = m_new * sl2;
-      for (int c = 0; c < a.BKV; c += 16) {
-        uint32_t v[16];
-        __syncwarp();
-        tmem_ld16(tS + (uint32_t)c, v);
-        tmem_ld_wait();
-        float p[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          p[i] = (kv0 + c + i < a.M) ? exp2f(__uint_as_float(v[i]) * sl2 - mb) : 0.f;
-        }
-        uint32_t w[8];
+      for (int i = 0; i < MAXC; ++i) {
+        const int ci = cg + i * CG;
+        if (ci < nchunk) {
+          uint32_t w[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          w[i] = pack_bf16(p[2 * i], p[2 * i + 1]);
-          // accumulate the ROUNDED probabilities so that l matches what the PV MMA sums
-          const float2 r = unpack_bf16(w[i]);
-          rs += r.x + r.y;
+          for (int e = 0; e < 8; ++e) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(sv[i][2 * e]), sl2, -mb));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(sv[i][2 * e + 1]), sl2, -mb));
+            rs += p0 + p1;
+            w[e] = pack_bf16(p0, p1);
+          }
+          uint8_t* pc = sP + (ci >> 2) * 16384;
+          const uint32_t c16 = (uint32_t)((ci & 3) * 2);
+          *reinterpret_cast<uint4*>(pc + sw128_off((uint32_t)row, c16)) = make_uint4(w[0], w[1], w[2], w[3]);
+          *reinterpret_cast<uint4*>(pc + sw128_off((uint32_t)row, c16 + 1)) = make_uint4(w[4], w[5], w[6], w[7]);
         }
-        uint8_t* pc = sP + (c >> 6) * 16384;
-        const uint32_t c16 = (uint32_t)((c & 63) >> 3);
-        *reinterpret_cast<uint4*>(pc + sw128_off((uint32_t)row, c16)) = make_uint4(w[0], w[1], w[2], w[3]);
-        *reinterpret_cast<uint4*>(pc + sw128_off((uint32_t)row, c16 + 1)) = make_uint4(w[4], w[5], w[6], w[7]);
       }
       l = l * alpha + rs;
       m = m_new;
-      // lazy rescale of the O accumulator (warp-uniform branch: tcgen05.ld/st are warp-collective)
+      // ---- lazy rescale of my chunks of the O accumulator (warp-uniform branch) ----
       if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
-        for (int c = 0; c < a.dpad; c += 16) {
+        for (int oc = cg; oc < ochunk; oc += CG) {
           uint32_t v[16];
-          tmem_ld16(tO + lane_base + (uint32_t)c, v);
+          tmem_ld16(tO + lane_base + (uint32_t)(oc * 16), v);
           tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-          tmem_st16(tO + lane_base + (uint32_t)c, v);
+          for (int e = 0; e < 16; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * alpha);
+          tmem_st16(tO + lane_base + (uint32_t)(oc * 16), v);
         }
         tmem_st_wait();
       }
@@ -229,12 +258,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
       tc_fence_before();
       mbar_arrive(p_ready);
     }
-    // epilogue
+    // ---- epilogue: combine row sums, normalise, store ----
+    sSum[cg * 128 + row] = l;
+    asm volatile("bar.sync 1, %0;" ::"n"(NSOFT) : "memory");
+    float lt = 0.f;
+#pragma unroll
+    for (int g = 0; g < CG; ++g) lt += sSum[g * 128 + row];
     mbar_wait(o_done, (uint32_t)((a.nblk - 1) & 1));
     tc_fence_after();
     const int n = q0 + row;
-    const float inv_l = 1.f / l;
-    for (int c = 0; c < a.dpad; c += 16) {
+    const float inv_l = 1.f / lt;
+    for (int oc = cg; oc < ochunk; oc += CG) {
+      const int c = oc * 16;
       uint32_t v[16];
       __syncwarp();
       tmem_ld16(tO + lane_base + (uint32_t)c, v);
@@ -253,7 +288,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
         }
       }
     }
-    if (n < a.N) a.LSE[((long long)b * a.H + h) * a.N + n] = m * a.scale + logf(l);
+    if (cg == 0 && n < a.N) a.LSE[((long long)b * a.H + h) * a.N + n] = m * a.scale + logf(lt);
   }
   tc_fence_before();
   __syncthreads();
@@ -296,7 +331,8 @@ __global__ void attn_delta_kernel(const bf16* __restrict__ O, const bf16* __rest
 // dQ kernel: CTA = (128-query tile, head, batch); loops over key blocks.
 //   TMEM: S [0,128) | dP [128,256) | dQ [256, 256+dpad)
 // =============================================================================================
-__global__ void __launch_bounds__(256, 1)
+template <int CG>
+__global__ void __launch_bounds__(128 + 128 * CG, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                    const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapdO,
                    const AttnArgs a) {
@@ -306,26 +342,28 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
   const int kv_tile = a.DC * a.BKV * 128;
   uint8_t* sQ = smem;
   uint8_t* sdO = sQ + q_bytes;
-  uint8_t* sK = sdO + q_bytes;
-  uint8_t* sV = sK + kv_tile;
-  uint8_t* sdS = sV + kv_tile;  // 2 x 16 KiB
+  uint8_t* sK = sdO + q_bytes;               // kst stages of {K tile, V tile}
+  uint8_t* sV = sK + a.kst * kv_tile;
+  uint8_t* sdS = sV + a.kst * kv_tile;  // 2 x 16 KiB
   uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + 32768);
   uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;
-  uint64_t* kv_empty = bars + 2;
-  uint64_t* sp_full = bars + 3;
-  uint64_t* ds_ready = bars + 4;
-  uint64_t* dq_done = bars + 5;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t* kv_full = bars + 1;   // [2]
+  uint64_t* kv_empty = bars + 3;  // [2]
+  uint64_t* sp_full = bars + 5;
+  uint64_t* ds_ready = bars + 6;
+  uint64_t* dq_done = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);
-    mbar_init(kv_full, 1);
-    mbar_init(kv_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
     mbar_init(sp_full, 1);
-    mbar_init(ds_ready, 128);
+    mbar_init(ds_ready, 128 * CG);
     mbar_init(dq_done, 1);
     fence_mbar_init();
   }
@@ -344,11 +382,12 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
         tma_load_4d(sdO + c * 16384, &mapdO, q_full, c * 64, h, q0, b);
       }
       for (int j = 0; j < a.nblk; ++j) {
-        mbar_wait(kv_empty, (uint32_t)((j & 1) ^ 1));
-        mbar_expect_tx(kv_full, (uint32_t)(2 * kv_tile));
+        const int st = j % a.kst;
+        mbar_wait(&kv_empty[st], (uint32_t)(((j / a.kst) & 1) ^ 1));
+        mbar_expect_tx(&kv_full[st], (uint32_t)(2 * kv_tile));
         for (int c = 0; c < a.DC; ++c) {
-          tma_load_4d(sK + c * a.BKV * 128, &mapK, kv_full, c * 64, h, j * a.BKV, b);
-          tma_load_4d(sV + c * a.BKV * 128, &mapV, kv_full, c * 64, h, j * a.BKV, b);
+          tma_load_4d(sK + st * kv_tile + c * a.BKV * 128, &mapK, &kv_full[st], c * 64, h, j * a.BKV, b);
+          tma_load_4d(sV + st * kv_tile + c * a.BKV * 128, &mapV, &kv_full[st], c * 64, h, j * a.BKV, b);
         }
       }
     }
@@ -358,58 +397,63 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
       const uint32_t idesc_o = umma_idesc_bf16((uint32_t)a.dpad, false, true);
       mbar_wait(q_full, 0);
       for (int j = 0; j < a.nblk; ++j) {
-        mbar_wait(kv_full, (uint32_t)(j & 1));
+        const int st = j % a.kst;
+        mbar_wait(&kv_full[st], (uint32_t)((j / a.kst) & 1));
         tc_fence_after();
-        mma_kmajor(tS, smem_u32(sQ), 16384, smem_u32(sK), a.BKV * 128, a.dh, a.DC, idesc_s);
-        mma_kmajor(tdP, smem_u32(sdO), 16384, smem_u32(sV), a.BKV * 128, a.dh, a.DC, idesc_s);
+        mma_kmajor(tS, smem_u32(sQ), 16384, smem_u32(sK + st * kv_tile), a.BKV * 128, a.dh, a.DC, idesc_s);
+        mma_kmajor(tdP, smem_u32(sdO), 16384, smem_u32(sV + st * kv_tile), a.BKV * 128, a.dh, a.DC, idesc_s);
         umma_commit(sp_full);
         mbar_wait(ds_ready, (uint32_t)(j & 1));
         tc_fence_after();
-        mma_pv(tdQ, smem_u32(sdS), smem_u32(sK), a.BKV * 128, a.BKV, idesc_o, j > 0 ? 1u : 0u);
-        umma_commit(kv_empty);
+        mma_pv(tdQ, smem_u32(sdS), smem_u32(sK + st * kv_tile), a.BKV * 128, a.BKV, idesc_o, j > 0 ? 1u : 0u);
+        umma_commit(&kv_empty[st]);
         umma_commit(dq_done);
       }
     }
   } else if (warp >= 4) {
-    const int ew = warp - 4;
+    constexpr int MAXC = 8 / CG;
+    const int ew = (warp - 4) & 3;
+    const int cg = (warp - 4) >> 2;
     const int row = ew * 32 + lane;
     const uint32_t lane_base = (uint32_t)(ew * 32) << 16;
     const int n = q0 + row;
     const float sl2 = a.scale * kLog2e;
     const long long sidx = ((long long)b * a.H + h) * a.N + n;
-    const float lse2 = (n < a.N) ? a.LSE[sidx] * kLog2e : 0.f;
-    const float dlt = (n < a.N) ? a.Dv[sidx] : 0.f;
+    const bool n_ok = n < a.N;
+    const float lse2 = n_ok ? a.LSE[sidx] * kLog2e : 0.f;
+    const float dlt = n_ok ? a.Dv[sidx] : 0.f;
+    const int nchunk = a.BKV >> 4;
+    const int ochunk = a.dpad >> 4;
     for (int j = 0; j < a.nblk; ++j) {
       mbar_wait(sp_full, (uint32_t)(j & 1));
       tc_fence_after();
       // sp_full(j) was committed after dQ-MMA(j-1) was issued, so the dS buffer is free here.
       const int kv0 = j * a.BKV;
-      for (int c = 0; c < a.BKV; c += 16) {
-        uint32_t s[16], dp[16];
-        __syncwarp();
-        tmem_ld16(tS + lane_base + (uint32_t)c, s);
-        tmem_ld16(tdP + lane_base + (uint32_t)c, dp);
-        tmem_ld_wait();
-        uint32_t w[8];
+      const bool partial = kv0 + a.BKV > a.M;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float d0 = 0.f, d1 = 0.f;
-          if (n < a.N) {
-            if (kv0 + c + 2 * i < a.M) {
-              const float p = exp2f(__uint_as_float(s[2 * i]) * sl2 - lse2);
-              d0 = p * (__uint_as_float(dp[2 * i]) - dlt) * a.scale;
-            }
-            if (kv0 + c + 2 * i + 1 < a.M) {
-              const float p = exp2f(__uint_as_float(s[2 * i + 1]) * sl2 - lse2);
-              d1 = p * (__uint_as_float(dp[2 * i + 1]) - dlt) * a.scale;
-            }
+      for (int i = 0; i < MAXC; ++i) {
+        const int ci = cg + i * CG;
+        if (ci < nchunk) {
+          uint32_t sreg[16], dp[16];
+          __syncwarp();
+          tmem_ld16(tS + lane_base + (uint32_t)(ci * 16), sreg);
+          tmem_ld16(tdP + lane_base + (uint32_t)(ci * 16), dp);
+          tmem_ld_wait();
+          uint32_t w[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float d0 = ex2_approx(fmaf(__uint_as_float(sreg[2 * e]), sl2, -lse2)) * (__uint_as_float(dp[2 * e]) - dlt) * a.scale;
+            float d1 = ex2_approx(fmaf(__uint_as_float(sreg[2 * e + 1]), sl2, -lse2)) *
+                       (__uint_as_float(dp[2 * e + 1]) - dlt) * a.scale;
+            if (!n_ok || (partial && kv0 + ci * 16 + 2 * e >= a.M)) d0 = 0.f;
+            if (!n_ok || (partial && kv0 + ci * 16 + 2 * e + 1 >= a.M)) d1 = 0.f;
+            w[e] = pack_bf16(d0, d1);
           }
-          w[i] = pack_bf16(d0, d1);
+          uint8_t* pc = sdS + (ci >> 2) * 16384;
+          const uint32_t c16 = (uint32_t)((ci & 3) * 2);
+          *reinterpret_cast<uint4*>(pc + sw128_off((uint32_t)row, c16)) = make_uint4(w[0], w[1], w[2], w[3]);
+          *reinterpret_cast<uint4*>(pc + sw128_off((uint32_t)row, c16 + 1)) = make_uint4(w[4], w[5], w[6], w[7]);
         }
-        uint8_t* pc = sdS + (c >> 6) * 16384;
-        const uint32_t c16 = (uint32_t)((c & 63) >> 3);
-        *reinterpret_cast<uint4*>(pc + sw128_off((uint32_t)row, c16)) = make_uint4(w[0], w[1], w[2], w[3]);
-        *reinterpret_cast<uint4*>(pc + sw128_off((uint32_t)row, c16 + 1)) = make_uint4(w[4], w[5], w[6], w[7]);
       }
       fence_proxy_async_smem();
       tc_fence_before();
@@ -417,12 +461,13 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
     }
     mbar_wait(dq_done, (uint32_t)((a.nblk - 1) & 1));
     tc_fence_after();
-    for (int c = 0; c < a.dpad; c += 16) {
+    for (int oc = cg; oc < ochunk; oc += CG) {
+      const int c = oc * 16;
       uint32_t v[16];
       __syncwarp();
       tmem_ld16(tdQ + lane_base + (uint32_t)c, v);
       tmem_ld_wait();
-      if (n < a.N) {
+      if (n_ok) {
         bf16* o = a.dQ + (long long)b * a.dq_bs + (long long)n * a.lddq + h * a.dh + c;
 #pragma unroll
         for (int i = 0; i < 16; i += 8) {
@@ -449,7 +494,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
 // dK/dV kernel: CTA = (128-key tile, head, batch); loops over query blocks of BKV (=BQ) rows.
 //   TMEM: Sᵀ [0,BQ) | dPᵀ [W,W+BQ) | dV [2W,2W+dpad) | dK [2W+dpad, 2W+2*dpad)   (W = BQ_max = 64 when dpad>128 else 128)
 // =============================================================================================
-__global__ void __launch_bounds__(256, 1)
+template <int CG>
+__global__ void __launch_bounds__(128 + 128 * CG, 1)
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                     const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapdO,
                     const AttnArgs a) {
@@ -460,29 +506,31 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
   const int q_tile = a.DC * BQ * 128;
   uint8_t* sK = smem;
   uint8_t* sV = sK + kv_bytes;
-  uint8_t* sQ = sV + kv_bytes;
-  uint8_t* sdO = sQ + q_tile;
-  uint8_t* sPT = sdO + q_tile;   // 2 x 16 KiB
+  uint8_t* sQ = sV + kv_bytes;                // kst stages of {Q tile, dO tile}
+  uint8_t* sdO = sQ + a.kst * q_tile;
+  uint8_t* sPT = sdO + a.kst * q_tile;   // 2 x 16 KiB
   uint8_t* sdST = sPT + 32768;   // 2 x 16 KiB
   float* sLSE = reinterpret_cast<float*>(sdST + 32768);  // [128]
   float* sD = sLSE + 128;                                // [128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sD + 128);
   uint64_t* kv_full = bars;
-  uint64_t* q_full = bars + 1;
-  uint64_t* q_empty = bars + 2;
-  uint64_t* sp_full = bars + 3;
-  uint64_t* ds_ready = bars + 4;
-  uint64_t* acc_done = bars + 5;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t* q_full = bars + 1;   // [2]
+  uint64_t* q_empty = bars + 3;  // [2]
+  uint64_t* sp_full = bars + 5;
+  uint64_t* ds_ready = bars + 6;
+  uint64_t* acc_done = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
   if (warp == 1 && lane == 0) {
     mbar_init(kv_full, 1);
-    mbar_init(q_full, 1);
-    mbar_init(q_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
+    }
     mbar_init(sp_full, 1);
-    mbar_init(ds_ready, 128);
+    mbar_init(ds_ready, 128 * CG);
     mbar_init(acc_done, 1);
     fence_mbar_init();
   }
@@ -502,11 +550,12 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
         tma_load_4d(sV + c * 16384, &mapV, kv_full, c * 64, h, k0, b);
       }
       for (int j = 0; j < a.nblk; ++j) {
-        mbar_wait(q_empty, (uint32_t)((j & 1) ^ 1));
-        mbar_expect_tx(q_full, (uint32_t)(2 * q_tile));
+        const int st = j % a.kst;
+        mbar_wait(&q_empty[st], (uint32_t)(((j / a.kst) & 1) ^ 1));
+        mbar_expect_tx(&q_full[st], (uint32_t)(2 * q_tile));
         for (int c = 0; c < a.DC; ++c) {
-          tma_load_4d(sQ + c * BQ * 128, &mapQ, q_full, c * 64, h, j * BQ, b);
-          tma_load_4d(sdO + c * BQ * 128, &mapdO, q_full, c * 64, h, j * BQ, b);
+          tma_load_4d(sQ + st * q_tile + c * BQ * 128, &mapQ, &q_full[st], c * 64, h, j * BQ, b);
+          tma_load_4d(sdO + st * q_tile + c * BQ * 128, &mapdO, &q_full[st], c * 64, h, j * BQ, b);
         }
       }
     }
@@ -516,72 +565,81 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
       const uint32_t idesc_o = umma_idesc_bf16((uint32_t)a.dpad, false, true);
       mbar_wait(kv_full, 0);
       for (int j = 0; j < a.nblk; ++j) {
-        mbar_wait(q_full, (uint32_t)(j & 1));
+        const int st = j % a.kst;
+        mbar_wait(&q_full[st], (uint32_t)((j / a.kst) & 1));
         tc_fence_after();
-        mma_kmajor(tST, smem_u32(sK), 16384, smem_u32(sQ), BQ * 128, a.dh, a.DC, idesc_s);
-        mma_kmajor(tdPT, smem_u32(sV), 16384, smem_u32(sdO), BQ * 128, a.dh, a.DC, idesc_s);
+        mma_kmajor(tST, smem_u32(sK), 16384, smem_u32(sQ + st * q_tile), BQ * 128, a.dh, a.DC, idesc_s);
+        mma_kmajor(tdPT, smem_u32(sV), 16384, smem_u32(sdO + st * q_tile), BQ * 128, a.dh, a.DC, idesc_s);
         umma_commit(sp_full);
         mbar_wait(ds_ready, (uint32_t)(j & 1));
         tc_fence_after();
-        mma_pv(tdV, smem_u32(sPT), smem_u32(sdO), BQ * 128, BQ, idesc_o, j > 0 ? 1u : 0u);
-        mma_pv(tdK, smem_u32(sdST), smem_u32(sQ), BQ * 128, BQ, idesc_o, j > 0 ? 1u : 0u);
-        umma_commit(q_empty);
+        mma_pv(tdV, smem_u32(sPT), smem_u32(sdO + st * q_tile), BQ * 128, BQ, idesc_o, j > 0 ? 1u : 0u);
+        mma_pv(tdK, smem_u32(sdST), smem_u32(sQ + st * q_tile), BQ * 128, BQ, idesc_o, j > 0 ? 1u : 0u);
+        umma_commit(&q_empty[st]);
         umma_commit(acc_done);
       }
     }
   } else if (warp >= 4) {
-    const int ew = warp - 4;
+    constexpr int MAXC = 8 / CG;
+    constexpr int NSOFT = 128 * CG;
+    const int ew = (warp - 4) & 3;
+    const int cg = (warp - 4) >> 2;
     const int row = ew * 32 + lane;  // key index within the tile
+    const int tid = threadIdx.x - 128;
     const uint32_t lane_base = (uint32_t)(ew * 32) << 16;
     const int kv = k0 + row;
     const bool kv_ok = kv < a.M;
     const float sl2 = a.scale * kLog2e;
     const long long sbase = ((long long)b * a.H + h) * a.N;
+    const int nchunk = BQ >> 4;
+    const int ochunk = a.dpad >> 4;
     for (int j = 0; j < a.nblk; ++j) {
-      // stage LSE / D of this query block (previous block's readers are past the named barrier below)
-      const int qn = j * BQ + row;
-      if (row < BQ) {
-        sLSE[row] = (qn < a.N) ? a.LSE[sbase + qn] * kLog2e : 0.f;
-        sD[row] = (qn < a.N) ? a.Dv[sbase + qn] : 0.f;
+      // stage LSE / D of this query block
+      const int qn = j * BQ + tid;
+      if (tid < BQ) {
+        sLSE[tid] = (qn < a.N) ? a.LSE[sbase + qn] * kLog2e : 0.f;
+        sD[tid] = (qn < a.N) ? a.Dv[sbase + qn] : 0.f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(NSOFT) : "memory");
       mbar_wait(sp_full, (uint32_t)(j & 1));
       tc_fence_after();
-      for (int c = 0; c < BQ; c += 16) {
-        uint32_t s[16], dp[16];
-        __syncwarp();
-        tmem_ld16(tST + lane_base + (uint32_t)c, s);
-        tmem_ld16(tdPT + lane_base + (uint32_t)c, dp);
-        tmem_ld_wait();
-        uint32_t wp[8], wd[8];
+      const bool partial = (j + 1) * BQ > a.N;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float p0 = 0.f, p1 = 0.f, d0 = 0.f, d1 = 0.f;
-          const int q_a = j * BQ + c + 2 * i;
-          if (kv_ok && q_a < a.N) {
-            p0 = exp2f(__uint_as_float(s[2 * i]) * sl2 - sLSE[c + 2 * i]);
-            d0 = p0 * (__uint_as_float(dp[2 * i]) - sD[c + 2 * i]) * a.scale;
+      for (int i = 0; i < MAXC; ++i) {
+        const int ci = cg + i * CG;
+        if (ci < nchunk) {
+          const int c = ci * 16;
+          uint32_t sreg[16], dp[16];
+          __syncwarp();
+          tmem_ld16(tST + lane_base + (uint32_t)c, sreg);
+          tmem_ld16(tdPT + lane_base + (uint32_t)c, dp);
+          tmem_ld_wait();
+          uint32_t wp[8], wd[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float p0 = ex2_approx(fmaf(__uint_as_float(sreg[2 * e]), sl2, -sLSE[c + 2 * e]));
+            float p1 = ex2_approx(fmaf(__uint_as_float(sreg[2 * e + 1]), sl2, -sLSE[c + 2 * e + 1]));
+            if (!kv_ok || (partial && j * BQ + c + 2 * e >= a.N)) p0 = 0.f;
+            if (!kv_ok || (partial && j * BQ + c + 2 * e + 1 >= a.N)) p1 = 0.f;
+            const float d0 = p0 * (__uint_as_float(dp[2 * e]) - sD[c + 2 * e]) * a.scale;
+            const float d1 = p1 * (__uint_as_float(dp[2 * e + 1]) - sD[c + 2 * e + 1]) * a.scale;
+            wp[e] = pack_bf16(p0, p1);
+            wd[e] = pack_bf16(d0, d1);
           }
-          if (kv_ok && q_a + 1 < a.N) {
-            p1 = exp2f(__uint_as_float(s[2 * i + 1]) * sl2 - sLSE[c + 2 * i + 1]);
-            d1 = p1 * (__uint_as_float(dp[2 * i + 1]) - sD[c + 2 * i + 1]) * a.scale;
-          }
-          wp[i] = pack_bf16(p0, p1);
-          wd[i] = pack_bf16(d0, d1);
+          const uint32_t c16 = (uint32_t)((ci & 3) * 2);
+          uint8_t* pp = sPT + (ci >> 2) * 16384;
+          uint8_t* pd = sdST + (ci >> 2) * 16384;
+          *reinterpret_cast<uint4*>(pp + sw128_off((uint32_t)row, c16)) = make_uint4(wp[0], wp[1], wp[2], wp[3]);
+          *reinterpret_cast<uint4*>(pp + sw128_off((uint32_t)row, c16 + 1)) = make_uint4(wp[4], wp[5], wp[6], wp[7]);
+          *reinterpret_cast<uint4*>(pd + sw128_off((uint32_t)row, c16)) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+          *reinterpret_cast<uint4*>(pd + sw128_off((uint32_t)row, c16 + 1)) = make_uint4(wd[4], wd[5], wd[6], wd[7]);
         }
-        const uint32_t c16 = (uint32_t)((c & 63) >> 3);
-        uint8_t* pp = sPT + (c >> 6) * 16384;
-        uint8_t* pd = sdST + (c >> 6) * 16384;
-        *reinterpret_cast<uint4*>(pp + sw128_off((uint32_t)row, c16)) = make_uint4(wp[0], wp[1], wp[2], wp[3]);
-        *reinterpret_cast<uint4*>(pp + sw128_off((uint32_t)row, c16 + 1)) = make_uint4(wp[4], wp[5], wp[6], wp[7]);
-        *reinterpret_cast<uint4*>(pd + sw128_off((uint32_t)row, c16)) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
-        *reinterpret_cast<uint4*>(pd + sw128_off((uint32_t)row, c16 + 1)) = make_uint4(wd[4], wd[5], wd[6], wd[7]);
       }
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(ds_ready);
-      // all 128 threads are done reading sLSE/sD for this block before the next block overwrites them
-      asm volatile("bar.sync 2, 128;" ::: "memory");
+      // everyone is done reading sLSE/sD of this block before the next block overwrites them
+      asm volatile("bar.sync 2, %0;" ::"n"(NSOFT) : "memory");
     }
     mbar_wait(acc_done, (uint32_t)((a.nblk - 1) & 1));
     tc_fence_after();
@@ -589,7 +647,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
       const uint32_t tacc = which == 0 ? tdV : tdK;
       bf16* base = which == 0 ? a.dV + (long long)b * a.dv_bs + (long long)kv * a.lddv
                               : a.dK + (long long)b * a.dk_bs + (long long)kv * a.lddk;
-      for (int c = 0; c < a.dpad; c += 16) {
+      for (int oc = cg; oc < ochunk; oc += CG) {
+        const int c = oc * 16;
         uint32_t v[16];
         __syncwarp();
         tmem_ld16(tacc + lane_base + (uint32_t)c, v);
@@ -629,6 +688,17 @@ static int make_head_map(CUtensorMap* m, const void* p, int dh, int H, int rows,
   return e4t_tmap_encode(m, p, 4, dims, str, box, 2);
 }
 static int round16(int x) { return (x + 15) / 16 * 16; }
+// column groups of softmax/dS warps per kernel (0 fwd, 1 dQ, 2 dKV); E4T_ATTN_CG="f,q,k" overrides for tuning
+static int attn_cg(int which) {
+  static int cfg[3] = {0, 0, 0};
+  if (cfg[0] == 0) {
+    cfg[0] = 4; cfg[1] = 4; cfg[2] = 4;
+    const char* e = getenv("E4T_ATTN_CG");
+    if (e) sscanf(e, "%d,%d,%d", &cfg[0], &cfg[1], &cfg[2]);
+    for (int i = 0; i < 3; ++i) if (cfg[i] != 2 && cfg[i] != 4) cfg[i] = 4;
+  }
+  return cfg[which];
+}
 
 static int attn_common_checks(int dh, long long ldq, long long ldk, long long ldv) {
   E4T_CHECK(dh % 8 == 0 && dh >= 8 && dh <= 192, "attention: head dim %d unsupported (need dh %% 8 == 0, <= 192)", dh);
@@ -656,14 +726,17 @@ extern "C" int e4t_attn_fwd(const void* Q, const void* K, const void* V, void* O
   if (int e = make_head_map(&mQ, Q, dh, H, N, B, ldq, q_bs, 128)) return e;
   if (int e = make_head_map(&mK, K, dh, H, M, B, ldk, k_bs, a.BKV)) return e;
   if (int e = make_head_map(&mV, V, dh, H, M, B, ldv, v_bs, a.BKV)) return e;
-  const size_t smem = (size_t)a.DC * 16384 + (size_t)2 * a.kst * a.DC * a.BKV * 128 + 32768 + 256 + 1024;
+  const int cg = attn_cg(0);
+  const size_t smem = (size_t)a.DC * 16384 + (size_t)2 * a.kst * a.DC * a.BKV * 128 + 32768 + 3 * 4 * 128 * 4 + 256 + 1024;
   static bool attr = false;
   if (!attr) {
-    E4T_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    E4T_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    E4T_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr = true;
   }
   E4T_CHECK(smem <= 227 * 1024, "e4t_attn_fwd: smem budget exceeded (%zu)", smem);
-  attn_fwd_kernel<<<dim3(cdiv(N, 128), H, B), 256, smem, st>>>(mQ, mK, mV, a);
+  if (cg == 4) attn_fwd_kernel<4><<<dim3(cdiv(N, 128), H, B), 128 + 128 * 4, smem, st>>>(mQ, mK, mV, a);
+  else attn_fwd_kernel<2><<<dim3(cdiv(N, 128), H, B), 128 + 128 * 2, smem, st>>>(mQ, mK, mV, a);
   E4T_COUNT_LAUNCH();
   E4T_LAUNCH_CHECK();
   return 0;
@@ -685,8 +758,10 @@ extern "C" int e4t_attn_bwd(const void* Q, const void* K, const void* V, const v
   E4T_LAUNCH_CHECK();
   static bool attr = false;
   if (!attr) {
-    E4T_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    E4T_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    E4T_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    E4T_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    E4T_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    E4T_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr = true;
   }
   AttnArgs a;
@@ -707,9 +782,13 @@ extern "C" int e4t_attn_bwd(const void* Q, const void* K, const void* V, const v
     if (int e = make_head_map(&mdO, dO, dh, H, N, B, lddo, do_bs, 128)) return e;
     if (int e = make_head_map(&mK, K, dh, H, M, B, ldk, k_bs, a.BKV)) return e;
     if (int e = make_head_map(&mV, V, dh, H, M, B, ldv, v_bs, a.BKV)) return e;
-    const size_t smem = (size_t)2 * a.DC * 16384 + (size_t)2 * a.DC * a.BKV * 128 + 32768 + 256 + 1024;
+    const size_t fixed = (size_t)2 * a.DC * 16384 + 32768 + 256 + 1024;
+    const size_t per_stage = (size_t)2 * a.DC * a.BKV * 128;
+    a.kst = (fixed + 2 * per_stage <= 227 * 1024 && a.nblk > 1) ? 2 : 1;
+    const size_t smem = fixed + a.kst * per_stage;
     E4T_CHECK(smem <= 227 * 1024, "e4t_attn_bwd(dQ): smem budget exceeded (%zu)", smem);
-    attn_bwd_dq_kernel<<<dim3(cdiv(N, 128), H, B), 256, smem, st>>>(mQ, mK, mV, mdO, a);
+    if (attn_cg(1) == 4) attn_bwd_dq_kernel<4><<<dim3(cdiv(N, 128), H, B), 128 + 128 * 4, smem, st>>>(mQ, mK, mV, mdO, a);
+    else attn_bwd_dq_kernel<2><<<dim3(cdiv(N, 128), H, B), 128 + 128 * 2, smem, st>>>(mQ, mK, mV, mdO, a);
     E4T_COUNT_LAUNCH();
     E4T_LAUNCH_CHECK();
   }
@@ -722,9 +801,13 @@ extern "C" int e4t_attn_bwd(const void* Q, const void* K, const void* V, const v
     if (int e = make_head_map(&mdO, dO, dh, H, N, B, lddo, do_bs, a.BKV)) return e;
     if (int e = make_head_map(&mK, K, dh, H, M, B, ldk, k_bs, 128)) return e;
     if (int e = make_head_map(&mV, V, dh, H, M, B, ldv, v_bs, 128)) return e;
-    const size_t smem = (size_t)2 * a.DC * 16384 + (size_t)2 * a.DC * a.BKV * 128 + 65536 + 1024 + 256 + 1024;
+    const size_t fixed = (size_t)2 * a.DC * 16384 + 65536 + 1024 + 256 + 1024;
+    const size_t per_stage = (size_t)2 * a.DC * a.BKV * 128;
+    a.kst = (fixed + 2 * per_stage <= 227 * 1024 && a.nblk > 1) ? 2 : 1;
+    const size_t smem = fixed + a.kst * per_stage;
     E4T_CHECK(smem <= 227 * 1024, "e4t_attn_bwd(dKV): smem budget exceeded (%zu)", smem);
-    attn_bwd_dkv_kernel<<<dim3(cdiv(M, 128), H, B), 256, smem, st>>>(mQ, mK, mV, mdO, a);
+    if (attn_cg(2) == 4) attn_bwd_dkv_kernel<4><<<dim3(cdiv(M, 128), H, B), 128 + 128 * 4, smem, st>>>(mQ, mK, mV, mdO, a);
+    else attn_bwd_dkv_kernel<2><<<dim3(cdiv(M, 128), H, B), 128 + 128 * 2, smem, st>>>(mQ, mK, mV, mdO, a);
     E4T_COUNT_LAUNCH();
     E4T_LAUNCH_CHECK();
   }

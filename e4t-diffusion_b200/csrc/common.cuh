@@ -223,5 +223,11 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
   __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(t);
 }
+// 2^x on the MUFU pipe, no denormal fix-up code (inputs here are <= 0 or bounded)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
 #endif  // __CUDACC__

@@ -261,14 +261,18 @@ wo_bwd_reduce_kernel(const float* __restrict__ dWeff, const float* __restrict__ 
     atomicAdd(&GTs[r], cs[r]);
   }
 }
-// Column mat-vec: out[j] = Σ_i M[i][j] x[i]   (M [n][n] row-major)  — thread per column, coalesced over j
+// Column mat-vec: out[j] += Σ_{i in chunk} M[i][j] x[i]   (M [n][n] row-major; out pre-zeroed)
+// grid (n/128 column tiles, row chunks of 32); coalesced over j, one atomic per (thread, chunk).
 __global__ void colmatvec_kernel(const float* __restrict__ M, const float* __restrict__ x, float* __restrict__ out,
                                  int n) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i0 = blockIdx.y * 32;
   if (j >= n) return;
   float acc = 0.f;
-  for (int i = 0; i < n; ++i) acc += M[(long)i * n + j] * x[i];
-  out[j] = acc;
+  const int i1 = min(n, i0 + 32);
+#pragma unroll 8
+  for (int i = i0; i < i1; ++i) acc += M[(long)i * n + j] * x[i];
+  atomicAdd(&out[j], acc);
 }
 // dM[i][j] = u[i] * w[j] + (t ? t[i] : 0)
 __global__ void outer_kernel(const float* __restrict__ u, const float* __restrict__ w, const float* __restrict__ t,
@@ -324,7 +328,7 @@ extern "C" int e4t_wo_bwd(const float* dWeff, const float* W, const float* v, co
   float* GTs = GTb + R;
   float* dvx = GTs + R;
   float* dvy = dvx + R;
-  E4T_CUDA(cudaMemsetAsync(GTb, 0, (size_t)2 * R * sizeof(float), st));
+  E4T_CUDA(cudaMemsetAsync(GTb, 0, (size_t)(2 * R + R + C) * sizeof(float), st));  // GTb, GTs, dvx, dvy
   wo_bwd_reduce_kernel<<<cdiv(C, 8), 256, (size_t)2 * R * sizeof(float), st>>>(dWeff, W, a, bc, b, s, Ga, Gbc, G1, GTb,
                                                                                GTs, C, R);
   E4T_COUNT_LAUNCH();
@@ -338,9 +342,9 @@ extern "C" int e4t_wo_bwd(const float* dWeff, const float* W, const float* v, co
   E4T_COUNT_LAUNCH();
   E4T_CUDA(cudaMemcpyAsync(dbc, GTs, (size_t)R * sizeof(float), cudaMemcpyDeviceToDevice, st));
   // dvy = Wrᵀ Ga ; dvx = Wcᵀ GTb
-  colmatvec_kernel<<<cdiv(C, 128), 128, 0, st>>>(Wr, Ga, dvy, C);
+  colmatvec_kernel<<<dim3(cdiv(C, 128), cdiv(C, 32)), 128, 0, st>>>(Wr, Ga, dvy, C);
   E4T_COUNT_LAUNCH();
-  colmatvec_kernel<<<cdiv(R, 128), 128, 0, st>>>(Wc, GTb, dvx, R);
+  colmatvec_kernel<<<dim3(cdiv(R, 128), cdiv(R, 32)), 128, 0, st>>>(Wc, GTb, dvx, R);
   E4T_COUNT_LAUNCH();
   wo_vec_grads_kernel<<<1, 256, 0, st>>>(dvx, dvy, w1, w2, v, dw1, db1, dw2, db2, dv, R, C);
   E4T_COUNT_LAUNCH();

@@ -86,7 +86,7 @@ class CrossAttention(nn.Module):
             flat += list(w.kernel_params())
         grad_on = torch.is_grad_enabled() and any(p.requires_grad for p in flat[len(lins):])
         key = (tuple((p._version, p.data_ptr()) for p in flat), grad_on, FN.WO_EPOCH if grad_on else -1,
-               FN.PARAM_EPOCH)
+               FN.PARAM_EPOCH if any(getattr(p, "_e4t_arena", False) for p in flat) else 0)
         ent = self._weff_cache.get(group)
         if ent is None or ent[0] != key:
             for l in lins:

@@ -203,7 +203,7 @@ class UNet2DConditionModel(ModelMixin, ConfigMixin):
             # all ResnetBlock2D time_emb_proj(silu(emb)) projections in ONE fp32 matmul
             resnets = self._resnets()
             ws = [r.time_emb_proj.weight for r in resnets]
-            key = tuple((w._version, w.data_ptr()) for w in ws) + (FN.PARAM_EPOCH,)
+            key = tuple((w._version, w.data_ptr()) for w in ws)
             cache = getattr(self, "_temb_cat", None)
             if cache is None or cache[0] != key:
                 cache = (key, torch.cat([w.detach().float() for w in ws], dim=0),

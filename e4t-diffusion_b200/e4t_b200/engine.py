@@ -73,6 +73,7 @@ class FlatAdamW:
                     o = off + (p.data_ptr() - base) // 4
                     p.data = self.arena[o:o + p.numel()].view(p.shape)
                     p.grad = self.grad[o:o + p.numel()].view(p.shape)
+                    p._e4t_arena = True
         self.step_count = 0
         FN.bump_param_epoch()
         # modules that cache views of re-homed storages refresh themselves lazily (E4TEncoder._stacked)

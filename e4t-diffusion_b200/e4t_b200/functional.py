@@ -34,7 +34,8 @@ def prepared(param, key, fn):
         except Exception:
             return fn(param.detach())
     ent = cache.get(key)
-    ver = (param._version, param.data_ptr(), param.device, PARAM_EPOCH if param.requires_grad else 0)
+    # PARAM_EPOCH only matters for parameters an arena optimiser updates behind torch's version counter
+    ver = (param._version, param.data_ptr(), param.device, PARAM_EPOCH if getattr(param, "_e4t_arena", False) else 0)
     if ent is None or ent[0] != ver:
         with torch.no_grad():
             ent = (ver, fn(param.detach()))
