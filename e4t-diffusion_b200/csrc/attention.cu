@@ -27,6 +27,8 @@ struct AttnArgs {
   int BKV;       // key/value block (fwd, dQ) or query block (dKV), multiple of 16
   int nblk;      // number of blocks looped over
   int kst;       // ring stages
+  int sbuf;      // fwd: S accumulator buffers in TMEM (2 = software pipelined, 1 = rely on 2 CTAs/SM)
+  int tmem_cols; // TMEM columns to allocate (256 lets two CTAs share an SM)
   float scale;   // dh^-0.5
   // pointers / strides (elements)
   bf16* O;  long long ldo, o_bs;
@@ -61,6 +63,20 @@ __device__ __forceinline__ void mma_pv(uint32_t d_tmem, uint32_t sP, uint32_t sV
   }
 }
 
+__device__ __forceinline__ float max32(const uint32_t* v, float mx) {
+#pragma unroll
+  for (int e = 0; e < 32; e += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(v[e]), __uint_as_float(v[e + 1])));
+  return mx;
+}
+// store 32 bf16 (packed in w[16]) of row `rowoff/128` at columns [col0, col0+32) of a K-major SWIZZLE_128B tile set
+__device__ __forceinline__ void sts_row32(uint8_t* tile, uint32_t rowoff, uint32_t r7, int col0, const uint32_t* w) {
+  uint8_t* pc = tile + (col0 >> 6) * 16384 + rowoff;
+  const uint32_t cb = (uint32_t)((col0 & 63) >> 3);
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    *reinterpret_cast<uint4*>(pc + (((cb + q) ^ r7) << 4)) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+}
+
 // =============================================================================================
 // Forward
 //   softmax warps are organised as CG column groups x 4 lane quadrants: warp (4 + 4*g + e) owns TMEM lanes
@@ -68,21 +84,21 @@ __device__ __forceinline__ void mma_pv(uint32_t d_tmem, uint32_t sP, uint32_t sV
 //   SM sub-partition has CG resident softmax warps to overlap MUFU / FMA / TMEM latencies.  Row maxima are exchanged
 //   through shared memory (double buffered), row sums are combined once at the end.
 // =============================================================================================
-template <int CG>
-__global__ void __launch_bounds__(128 + 128 * CG, 1)
+template <int CG, int OCC>
+__global__ void __launch_bounds__(128 + 128 * CG, OCC)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                 const __grid_constant__ CUtensorMap mapV, const AttnArgs a) {
   constexpr int MAXC = 8 / CG;  // 16-column chunks per thread and block
   constexpr int NSOFT = 128 * CG;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps shared-space provenance
   const int q_bytes = a.DC * 16384;
   const int kv_tile = a.DC * a.BKV * 128;
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + q_bytes;
   uint8_t* sV = sK + a.kst * kv_tile;
   uint8_t* sP = sV + a.kst * kv_tile;  // 2 x 16 KiB
-  float* sMax = reinterpret_cast<float*>(sP + 32768);  // [2][CG][128]
+  float* sMax = reinterpret_cast<float*>(sP + ((a.BKV + 63) >> 6) * 16384);  // [2][CG][128]
   float* sSum = sMax + 2 * CG * 128;                   // [CG][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sSum + CG * 128);
   uint64_t* q_full = bars;
@@ -111,12 +127,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
     mbar_init(o_done, 1);
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tS0 = tmem, tO = tmem + 256;
+  const uint32_t tS0 = tmem, tO = tmem + (uint32_t)a.sbuf * 128u;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -147,22 +163,29 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
       umma_commit(&k_empty[0]);
       umma_commit(&s_full[0]);
       for (int j = 0; j < a.nblk; ++j) {
-        if (j + 1 < a.nblk) {
-          const int jn = j + 1, st = jn % a.kst;
-          mbar_wait(&k_full[st], (uint32_t)((jn / a.kst) & 1));
-          tc_fence_after();
-          mma_kmajor(tS0 + (uint32_t)(jn & 1) * 128u, smem_u32(sQ), 16384, smem_u32(sK + st * kv_tile), a.BKV * 128,
-                     a.dh, a.DC, idesc_s);
-          umma_commit(&k_empty[st]);
-          umma_commit(&s_full[jn & 1]);
+        // sbuf == 2: S_{j+1} is issued BEFORE waiting for P_j (its TMEM buffer is the other one);
+        // sbuf == 1: S_{j+1} may only overwrite the single buffer after softmax_j has read it (p_ready(j)).
+        for (int pass = 0; pass < 2; ++pass) {
+          const bool issue_s = (a.sbuf == 2) ? (pass == 0) : (pass == 1);
+          if (issue_s && j + 1 < a.nblk) {
+            const int jn = j + 1, st = jn % a.kst;
+            mbar_wait(&k_full[st], (uint32_t)((jn / a.kst) & 1));
+            tc_fence_after();
+            mma_kmajor(tS0 + (uint32_t)(jn & (a.sbuf - 1)) * 128u, smem_u32(sQ), 16384, smem_u32(sK + st * kv_tile),
+                       a.BKV * 128, a.dh, a.DC, idesc_s);
+            umma_commit(&k_empty[st]);
+            umma_commit(&s_full[jn & (a.sbuf - 1)]);
+          }
+          if (pass == 0) {
+            const int st = j % a.kst;
+            mbar_wait(p_ready, (uint32_t)(j & 1));
+            mbar_wait(&v_full[st], (uint32_t)((j / a.kst) & 1));
+            tc_fence_after();
+            mma_pv(tO, smem_u32(sP), smem_u32(sV + st * kv_tile), a.BKV * 128, a.BKV, idesc_o, j > 0 ? 1u : 0u);
+            umma_commit(&v_empty[st]);
+            umma_commit(o_done);
+          }
         }
-        const int st = j % a.kst;
-        mbar_wait(p_ready, (uint32_t)(j & 1));
-        mbar_wait(&v_full[st], (uint32_t)((j / a.kst) & 1));
-        tc_fence_after();
-        mma_pv(tO, smem_u32(sP), smem_u32(sV + st * kv_tile), a.BKV * 128, a.BKV, idesc_o, j > 0 ? 1u : 0u);
-        umma_commit(&v_empty[st]);
-        umma_commit(o_done);
       }
     }
   } else if (warp >= 4) {
@@ -174,36 +197,112 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
     const int nchunk = a.BKV >> 4;
     const int ochunk = a.dpad >> 4;
     float m = -INFINITY, l = 0.f;
+    const uint32_t rowoff = (uint32_t)row * 128u, r7 = (uint32_t)row & 7u;
     for (int j = 0; j < a.nblk; ++j) {
-      const uint32_t tS = tS0 + (uint32_t)(j & 1) * 128u + lane_base;
-      mbar_wait(&s_full[j & 1], (uint32_t)((j >> 1) & 1));
+      const uint32_t tS = tS0 + (uint32_t)(j & (a.sbuf - 1)) * 128u + lane_base;
+      mbar_wait(&s_full[j & (a.sbuf - 1)], (uint32_t)((j / a.sbuf) & 1));
       tc_fence_after();
-      const int kv0 = j * a.BKV;
-      // ---- load my column chunks of S (single TMEM pass) ----
-      uint32_t sv[MAXC][16];
-      __syncwarp();
+      if (a.BKV == 128 && (j + 1) * 128 <= a.M) {
+        // ======== fast path: full 128-key block; each thread owns NC chunks of 32 columns ========
+        constexpr int NC = 4 / CG;
+        uint32_t v[32];
+        float mx = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < MAXC; ++i) {
-        const int ci = cg + i * CG;
-        if (ci < nchunk) tmem_ld16(tS + (uint32_t)(ci * 16), sv[i]);
+        for (int i = 0; i < NC; ++i) {
+          __syncwarp();
+          tmem_ld32(tS + (uint32_t)((cg + i * CG) * 32), v);
+          tmem_ld_wait();
+          mx = max32(v, mx);
+        }
+        float* smx = sMax + (j & 1) * CG * 128;
+        smx[cg * 128 + row] = mx;
+        asm volatile("bar.sync 1, %0;" ::"n"(NSOFT) : "memory");
+#pragma unroll
+        for (int g = 0; g < CG; ++g) mx = fmaxf(mx, smx[g * 128 + row]);
+        const float m_new = fmaxf(m, mx);
+        const float alpha = ex2_approx((m - m_new) * sl2);
+        if (j > 0) {
+          mbar_wait(o_done, (uint32_t)((j - 1) & 1));
+          tc_fence_after();
+        }
+        float rs0 = 0.f, rs1 = 0.f;
+        const float mb = m_new * sl2;
+#pragma unroll
+        for (int i = 0; i < NC; ++i) {
+          const int col0 = (cg + i * CG) * 32;
+          if (NC > 1) {
+            __syncwarp();
+            tmem_ld32(tS + (uint32_t)col0, v);
+            tmem_ld_wait();
+          }
+          uint32_t w[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * e]), sl2, -mb));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * e + 1]), sl2, -mb));
+            rs0 += p0;
+            rs1 += p1;
+            w[e] = pack_bf16(p0, p1);
+          }
+          sts_row32(sP, rowoff, r7, col0, w);
+        }
+        l = l * alpha + (rs0 + rs1);
+        m = m_new;
+        if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
+          for (int oc = cg; oc < ochunk; oc += CG) {
+            uint32_t ov[16];
+            tmem_ld16(tO + lane_base + (uint32_t)(oc * 16), ov);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) ov[e] = __float_as_uint(__uint_as_float(ov[e]) * alpha);
+            tmem_st16(tO + lane_base + (uint32_t)(oc * 16), ov);
+          }
+          tmem_st_wait();
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(p_ready);
+        continue;
       }
-      tmem_ld_wait();
+      // ======== generic path (ragged / short key blocks) ========
+      const int kv0 = j * a.BKV;
+      // ---- row max over my column chunks (OCC==1: S kept in registers; OCC==2: low-register two-pass) ----
+      uint32_t sv[OCC == 1 ? MAXC : 1][16];
       const bool partial = kv0 + a.BKV > a.M;  // only the last block can be ragged
       float mx = -INFINITY;
+      if (OCC == 1) {
+        __syncwarp();
 #pragma unroll
-      for (int i = 0; i < MAXC; ++i) {
-        const int ci = cg + i * CG;
-        if (ci < nchunk) {
-          if (!partial) {
+        for (int i = 0; i < MAXC; ++i) {
+          const int ci = cg + i * CG;
+          if (ci < nchunk) tmem_ld16(tS + (uint32_t)(ci * 16), sv[OCC == 1 ? i : 0]);
+        }
+        tmem_ld_wait();
 #pragma unroll
-            for (int e = 0; e < 16; ++e) mx = fmaxf(mx, __uint_as_float(sv[i][e]));
-          } else {
+        for (int i = 0; i < MAXC; ++i) {
+          const int ci = cg + i * CG;
+          if (ci < nchunk) {
+            uint32_t* svi = sv[OCC == 1 ? i : 0];
+            if (!partial) {
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              if (kv0 + ci * 16 + e >= a.M) sv[i][e] = 0xff800000u;  // -inf
-              mx = fmaxf(mx, __uint_as_float(sv[i][e]));
+              for (int e = 0; e < 16; ++e) mx = fmaxf(mx, __uint_as_float(svi[e]));
+            } else {
+#pragma unroll
+              for (int e = 0; e < 16; ++e) {
+                if (kv0 + ci * 16 + e >= a.M) svi[e] = 0xff800000u;  // -inf
+                mx = fmaxf(mx, __uint_as_float(svi[e]));
+              }
             }
           }
+        }
+      } else {
+        for (int ci = cg; ci < nchunk; ci += CG) {
+          __syncwarp();
+          tmem_ld16(tS + (uint32_t)(ci * 16), sv[0]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 16; ++e)
+            if (!partial || kv0 + ci * 16 + e < a.M) mx = fmaxf(mx, __uint_as_float(sv[0][e]));
         }
       }
       // ---- exchange row maxima between the column groups ----
@@ -226,11 +325,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
       for (int i = 0; i < MAXC; ++i) {
         const int ci = cg + i * CG;
         if (ci < nchunk) {
+          uint32_t* svi = sv[OCC == 1 ? i : 0];
+          if (OCC != 1) {
+            __syncwarp();
+            tmem_ld16(tS + (uint32_t)(ci * 16), svi);
+            tmem_ld_wait();
+            if (partial) {
+#pragma unroll
+              for (int e = 0; e < 16; ++e)
+                if (kv0 + ci * 16 + e >= a.M) svi[e] = 0xff800000u;
+            }
+          }
           uint32_t w[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            const float p0 = ex2_approx(fmaf(__uint_as_float(sv[i][2 * e]), sl2, -mb));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(sv[i][2 * e + 1]), sl2, -mb));
+            const float p0 = ex2_approx(fmaf(__uint_as_float(svi[2 * e]), sl2, -mb));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(svi[2 * e + 1]), sl2, -mb));
             rs += p0 + p1;
             w[e] = pack_bf16(p0, p1);
           }
@@ -294,7 +404,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem, 512);
+    tmem_dealloc(tmem, (uint32_t)a.tmem_cols);
   }
 }
 
@@ -331,13 +441,13 @@ __global__ void attn_delta_kernel(const bf16* __restrict__ O, const bf16* __rest
 // dQ kernel: CTA = (128-query tile, head, batch); loops over key blocks.
 //   TMEM: S [0,128) | dP [128,256) | dQ [256, 256+dpad)
 // =============================================================================================
-template <int CG>
-__global__ void __launch_bounds__(128 + 128 * CG, 1)
+template <int CG, int OCC>
+__global__ void __launch_bounds__(128 + 128 * CG, OCC)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                    const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapdO,
                    const AttnArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps shared-space provenance
   const int q_bytes = a.DC * 16384;
   const int kv_tile = a.DC * a.BKV * 128;
   uint8_t* sQ = smem;
@@ -345,7 +455,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
   uint8_t* sK = sdO + q_bytes;               // kst stages of {K tile, V tile}
   uint8_t* sV = sK + a.kst * kv_tile;
   uint8_t* sdS = sV + a.kst * kv_tile;  // 2 x 16 KiB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + 32768);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sdS + ((a.BKV + 63) >> 6) * 16384);
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;   // [2]
   uint64_t* kv_empty = bars + 3;  // [2]
@@ -367,12 +477,12 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
     mbar_init(dq_done, 1);
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tS = tmem, tdP = tmem + 128, tdQ = tmem + 256;
+  const uint32_t tS = tmem, tdP = tmem + (uint32_t)a.BKV, tdQ = tmem + 2u * (uint32_t)a.BKV;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -420,14 +530,39 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
     const float sl2 = a.scale * kLog2e;
     const long long sidx = ((long long)b * a.H + h) * a.N + n;
     const bool n_ok = n < a.N;
-    const float lse2 = n_ok ? a.LSE[sidx] * kLog2e : 0.f;
-    const float dlt = n_ok ? a.Dv[sidx] : 0.f;
+    const float lse2 = n_ok ? a.LSE[sidx] * kLog2e : INFINITY;   // rows past N: p = 2^-inf = 0
+    const float dlt_s = n_ok ? a.Dv[sidx] * a.scale : 0.f;
     const int nchunk = a.BKV >> 4;
     const int ochunk = a.dpad >> 4;
+    const uint32_t rowoff = (uint32_t)row * 128u, r7 = (uint32_t)row & 7u;
     for (int j = 0; j < a.nblk; ++j) {
       mbar_wait(sp_full, (uint32_t)(j & 1));
       tc_fence_after();
       // sp_full(j) was committed after dQ-MMA(j-1) was issued, so the dS buffer is free here.
+      if ((a.BKV & 31) == 0 && (j + 1) * a.BKV <= a.M) {
+        // ======== fast path: full key block, 32-column chunks ========
+        const int nc32 = a.BKV >> 5;
+        for (int c = cg; c < nc32; c += CG) {
+          uint32_t sreg[32], dp[32], w[16];
+          __syncwarp();
+          tmem_ld32(tS + lane_base + (uint32_t)(c * 32), sreg);
+          tmem_ld32(tdP + lane_base + (uint32_t)(c * 32), dp);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const float d0 = ex2_approx(fmaf(__uint_as_float(sreg[2 * e]), sl2, -lse2)) *
+                             fmaf(__uint_as_float(dp[2 * e]), a.scale, -dlt_s);
+            const float d1 = ex2_approx(fmaf(__uint_as_float(sreg[2 * e + 1]), sl2, -lse2)) *
+                             fmaf(__uint_as_float(dp[2 * e + 1]), a.scale, -dlt_s);
+            w[e] = pack_bf16(d0, d1);
+          }
+          sts_row32(sdS, rowoff, r7, c * 32, w);
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(ds_ready);
+        continue;
+      }
       const int kv0 = j * a.BKV;
       const bool partial = kv0 + a.BKV > a.M;
 #pragma unroll
@@ -442,11 +577,14 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
           uint32_t w[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            float d0 = ex2_approx(fmaf(__uint_as_float(sreg[2 * e]), sl2, -lse2)) * (__uint_as_float(dp[2 * e]) - dlt) * a.scale;
+            float d0 = ex2_approx(fmaf(__uint_as_float(sreg[2 * e]), sl2, -lse2)) *
+                       fmaf(__uint_as_float(dp[2 * e]), a.scale, -dlt_s);
             float d1 = ex2_approx(fmaf(__uint_as_float(sreg[2 * e + 1]), sl2, -lse2)) *
-                       (__uint_as_float(dp[2 * e + 1]) - dlt) * a.scale;
-            if (!n_ok || (partial && kv0 + ci * 16 + 2 * e >= a.M)) d0 = 0.f;
-            if (!n_ok || (partial && kv0 + ci * 16 + 2 * e + 1 >= a.M)) d1 = 0.f;
+                       fmaf(__uint_as_float(dp[2 * e + 1]), a.scale, -dlt_s);
+            if (partial) {
+              if (kv0 + ci * 16 + 2 * e >= a.M) d0 = 0.f;
+              if (kv0 + ci * 16 + 2 * e + 1 >= a.M) d1 = 0.f;
+            }
             w[e] = pack_bf16(d0, d1);
           }
           uint8_t* pc = sdS + (ci >> 2) * 16384;
@@ -486,7 +624,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem, 512);
+    tmem_dealloc(tmem, (uint32_t)a.tmem_cols);
   }
 }
 
@@ -494,13 +632,13 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_consta
 // dK/dV kernel: CTA = (128-key tile, head, batch); loops over query blocks of BKV (=BQ) rows.
 //   TMEM: Sᵀ [0,BQ) | dPᵀ [W,W+BQ) | dV [2W,2W+dpad) | dK [2W+dpad, 2W+2*dpad)   (W = BQ_max = 64 when dpad>128 else 128)
 // =============================================================================================
-template <int CG>
-__global__ void __launch_bounds__(128 + 128 * CG, 1)
+template <int CG, int OCC>
+__global__ void __launch_bounds__(128 + 128 * CG, OCC)
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                     const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapdO,
                     const AttnArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps shared-space provenance
   const int BQ = a.BKV;
   const int kv_bytes = a.DC * 16384;
   const int q_tile = a.DC * BQ * 128;
@@ -509,8 +647,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
   uint8_t* sQ = sV + kv_bytes;                // kst stages of {Q tile, dO tile}
   uint8_t* sdO = sQ + a.kst * q_tile;
   uint8_t* sPT = sdO + a.kst * q_tile;   // 2 x 16 KiB
-  uint8_t* sdST = sPT + 32768;   // 2 x 16 KiB
-  float* sLSE = reinterpret_cast<float*>(sdST + 32768);  // [128]
+  uint8_t* sdST = sPT + ((BQ + 63) >> 6) * 16384;
+  float* sLSE = reinterpret_cast<float*>(sdST + ((BQ + 63) >> 6) * 16384);  // [128]
   float* sD = sLSE + 128;                                // [128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sD + 128);
   uint64_t* kv_full = bars;
@@ -534,12 +672,12 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
     mbar_init(acc_done, 1);
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t sp_cols = a.dpad > 128 ? 64u : 128u;
+  const uint32_t sp_cols = (uint32_t)((BQ + 31) & ~31);
   const uint32_t tST = tmem, tdPT = tmem + sp_cols, tdV = tmem + 2 * sp_cols, tdK = tmem + 2 * sp_cols + (uint32_t)a.dpad;
 
   if (warp == 0) {
@@ -589,7 +727,11 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
     const uint32_t lane_base = (uint32_t)(ew * 32) << 16;
     const int kv = k0 + row;
     const bool kv_ok = kv < a.M;
+    const bool kv_ok_warp = (k0 + ew * 32 + 31) < a.M;   // warp-uniform
+    const uint32_t rowoff = (uint32_t)row * 128u, r7 = (uint32_t)row & 7u;
     const float sl2 = a.scale * kLog2e;
+    // keys past M: S^T row is 0 (zero-filled K) -> use slope 0 and rely on p = 2^(-lse) ... no: force p = 0 below
+    const float sl2_row = sl2;
     const long long sbase = ((long long)b * a.H + h) * a.N;
     const int nchunk = BQ >> 4;
     const int ochunk = a.dpad >> 4;
@@ -597,13 +739,47 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
       // stage LSE / D of this query block
       const int qn = j * BQ + tid;
       if (tid < BQ) {
-        sLSE[tid] = (qn < a.N) ? a.LSE[sbase + qn] * kLog2e : 0.f;
-        sD[tid] = (qn < a.N) ? a.Dv[sbase + qn] : 0.f;
+        sLSE[tid] = (qn < a.N) ? a.LSE[sbase + qn] * kLog2e : INFINITY;   // queries past N: p = 0
+        sD[tid] = (qn < a.N) ? a.Dv[sbase + qn] * a.scale : 0.f;
       }
       asm volatile("bar.sync 1, %0;" ::"n"(NSOFT) : "memory");
       mbar_wait(sp_full, (uint32_t)(j & 1));
       tc_fence_after();
-      const bool partial = (j + 1) * BQ > a.N;
+      if ((BQ & 31) == 0 && kv_ok_warp) {
+        // ======== fast path: 32-column chunks, whole warp inside the key range (ragged queries are handled by
+        // sLSE = +inf) ========
+        const int nc32 = BQ >> 5;
+        for (int c32 = cg; c32 < nc32; c32 += CG) {
+          const int c = c32 * 32;
+          uint32_t sreg[32], dp[32], wp[16], wd[16];
+          __syncwarp();
+          tmem_ld32(tST + lane_base + (uint32_t)c, sreg);
+          tmem_ld32(tdPT + lane_base + (uint32_t)c, dp);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 16; e += 2) {
+            const float4 ls = *reinterpret_cast<const float4*>(&sLSE[c + 2 * e]);
+            const float4 dd = *reinterpret_cast<const float4*>(&sD[c + 2 * e]);
+            const float p0 = ex2_approx(fmaf(__uint_as_float(sreg[2 * e]), sl2, -ls.x));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(sreg[2 * e + 1]), sl2, -ls.y));
+            const float p2 = ex2_approx(fmaf(__uint_as_float(sreg[2 * e + 2]), sl2, -ls.z));
+            const float p3 = ex2_approx(fmaf(__uint_as_float(sreg[2 * e + 3]), sl2, -ls.w));
+            wp[e] = pack_bf16(p0, p1);
+            wp[e + 1] = pack_bf16(p2, p3);
+            wd[e] = pack_bf16(p0 * fmaf(__uint_as_float(dp[2 * e]), a.scale, -dd.x),
+                              p1 * fmaf(__uint_as_float(dp[2 * e + 1]), a.scale, -dd.y));
+            wd[e + 1] = pack_bf16(p2 * fmaf(__uint_as_float(dp[2 * e + 2]), a.scale, -dd.z),
+                                  p3 * fmaf(__uint_as_float(dp[2 * e + 3]), a.scale, -dd.w));
+          }
+          sts_row32(sPT, rowoff, r7, c, wp);
+          sts_row32(sdST, rowoff, r7, c, wd);
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(ds_ready);
+        asm volatile("bar.sync 2, %0;" ::"n"(NSOFT) : "memory");
+        continue;
+      }
 #pragma unroll
       for (int i = 0; i < MAXC; ++i) {
         const int ci = cg + i * CG;
@@ -617,14 +793,14 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
           uint32_t wp[8], wd[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            float p0 = ex2_approx(fmaf(__uint_as_float(sreg[2 * e]), sl2, -sLSE[c + 2 * e]));
-            float p1 = ex2_approx(fmaf(__uint_as_float(sreg[2 * e + 1]), sl2, -sLSE[c + 2 * e + 1]));
-            if (!kv_ok || (partial && j * BQ + c + 2 * e >= a.N)) p0 = 0.f;
-            if (!kv_ok || (partial && j * BQ + c + 2 * e + 1 >= a.N)) p1 = 0.f;
-            const float d0 = p0 * (__uint_as_float(dp[2 * e]) - sD[c + 2 * e]) * a.scale;
-            const float d1 = p1 * (__uint_as_float(dp[2 * e + 1]) - sD[c + 2 * e + 1]) * a.scale;
-            wp[e] = pack_bf16(p0, p1);
-            wd[e] = pack_bf16(d0, d1);
+            const float2 ls = *reinterpret_cast<const float2*>(&sLSE[c + 2 * e]);
+            const float2 dd = *reinterpret_cast<const float2*>(&sD[c + 2 * e]);
+            float p0 = ex2_approx(fmaf(__uint_as_float(sreg[2 * e]), sl2_row, -ls.x));
+            float p1 = ex2_approx(fmaf(__uint_as_float(sreg[2 * e + 1]), sl2_row, -ls.y));
+            const float d0 = p0 * fmaf(__uint_as_float(dp[2 * e]), a.scale, -dd.x);
+            const float d1 = p1 * fmaf(__uint_as_float(dp[2 * e + 1]), a.scale, -dd.y);
+            wp[e] = kv_ok ? pack_bf16(p0, p1) : 0u;
+            wd[e] = kv_ok ? pack_bf16(d0, d1) : 0u;
           }
           const uint32_t c16 = (uint32_t)((ci & 3) * 2);
           uint8_t* pp = sPT + (ci >> 2) * 16384;
@@ -673,7 +849,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem, 512);
+    tmem_dealloc(tmem, (uint32_t)a.tmem_cols);
   }
 }
 
@@ -690,11 +866,11 @@ static int make_head_map(CUtensorMap* m, const void* p, int dh, int H, int rows,
 static int round16(int x) { return (x + 15) / 16 * 16; }
 // column groups of softmax/dS warps per kernel (0 fwd, 1 dQ, 2 dKV); E4T_ATTN_CG="f,q,k" overrides for tuning
 static int attn_cg(int which) {
-  static int cfg[3] = {0, 0, 0};
+  static int cfg[4] = {0, 0, 0, 1};   // [3]: allow the two-CTAs-per-SM variants
   if (cfg[0] == 0) {
     cfg[0] = 4; cfg[1] = 4; cfg[2] = 4;
     const char* e = getenv("E4T_ATTN_CG");
-    if (e) sscanf(e, "%d,%d,%d", &cfg[0], &cfg[1], &cfg[2]);
+    if (e) sscanf(e, "%d,%d,%d,%d", &cfg[0], &cfg[1], &cfg[2], &cfg[3]);
     for (int i = 0; i < 3; ++i) if (cfg[i] != 2 && cfg[i] != 4) cfg[i] = 4;
   }
   return cfg[which];
@@ -719,7 +895,11 @@ extern "C" int e4t_attn_fwd(const void* Q, const void* K, const void* V, void* O
   a.dpad = round16(dh);
   a.BKV = M >= 128 ? 128 : round16(M);
   a.nblk = cdiv(M, a.BKV);
-  a.kst = a.DC >= 3 ? 1 : 2;
+  // dh <= 64 and a long key axis: two CTAs per SM (256 TMEM columns, single S buffer, single K/V stage)
+  const bool occ2 = (a.DC == 1 && a.nblk >= 4 && attn_cg(3) != 0);
+  a.kst = (a.DC >= 3 || occ2) ? 1 : 2;
+  a.sbuf = occ2 ? 1 : 2;
+  a.tmem_cols = occ2 ? 256 : 512;
   a.scale = scale;
   a.O = (bf16*)O; a.ldo = ldo; a.o_bs = o_bs; a.LSE = LSE;
   CUtensorMap mQ, mK, mV;
@@ -727,16 +907,19 @@ extern "C" int e4t_attn_fwd(const void* Q, const void* K, const void* V, void* O
   if (int e = make_head_map(&mK, K, dh, H, M, B, ldk, k_bs, a.BKV)) return e;
   if (int e = make_head_map(&mV, V, dh, H, M, B, ldv, v_bs, a.BKV)) return e;
   const int cg = attn_cg(0);
-  const size_t smem = (size_t)a.DC * 16384 + (size_t)2 * a.kst * a.DC * a.BKV * 128 + 32768 + 3 * 4 * 128 * 4 + 256 + 1024;
+  const size_t smem = (size_t)a.DC * 16384 + (size_t)2 * a.kst * a.DC * a.BKV * 128 + (size_t)cdiv(a.BKV, 64) * 16384 +
+                      3 * 4 * 128 * 4 + 256 + 1024;
   static bool attr = false;
   if (!attr) {
-    E4T_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    E4T_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    E4T_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    E4T_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    E4T_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
     attr = true;
   }
-  E4T_CHECK(smem <= 227 * 1024, "e4t_attn_fwd: smem budget exceeded (%zu)", smem);
-  if (cg == 4) attn_fwd_kernel<4><<<dim3(cdiv(N, 128), H, B), 128 + 128 * 4, smem, st>>>(mQ, mK, mV, a);
-  else attn_fwd_kernel<2><<<dim3(cdiv(N, 128), H, B), 128 + 128 * 2, smem, st>>>(mQ, mK, mV, a);
+  E4T_CHECK(smem <= (occ2 ? 113 : 227) * 1024, "e4t_attn_fwd: smem budget exceeded (%zu)", smem);
+  if (occ2) attn_fwd_kernel<2, 2><<<dim3(cdiv(N, 128), H, B), 128 + 128 * 2, smem, st>>>(mQ, mK, mV, a);
+  else if (cg == 4) attn_fwd_kernel<4, 1><<<dim3(cdiv(N, 128), H, B), 128 + 128 * 4, smem, st>>>(mQ, mK, mV, a);
+  else attn_fwd_kernel<2, 1><<<dim3(cdiv(N, 128), H, B), 128 + 128 * 2, smem, st>>>(mQ, mK, mV, a);
   E4T_COUNT_LAUNCH();
   E4T_LAUNCH_CHECK();
   return 0;
@@ -758,10 +941,12 @@ extern "C" int e4t_attn_bwd(const void* Q, const void* K, const void* V, const v
   E4T_LAUNCH_CHECK();
   static bool attr = false;
   if (!attr) {
-    E4T_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    E4T_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    E4T_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    E4T_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    E4T_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    E4T_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    E4T_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+    E4T_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    E4T_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    E4T_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
     attr = true;
   }
   AttnArgs a;
@@ -775,39 +960,47 @@ extern "C" int e4t_attn_bwd(const void* Q, const void* K, const void* V, const v
   a.dK = (bf16*)dK; a.lddk = lddk; a.dk_bs = dk_bs;
   a.dV = (bf16*)dV; a.lddv = lddv; a.dv_bs = dv_bs;
   {  // dQ
-    a.BKV = M >= 128 ? 128 : round16(M);
+    const bool occ2 = (a.DC == 1 && M >= 512 && attn_cg(3) != 0);   // two CTAs/SM: 64-wide key blocks, 256 TMEM cols
+    a.BKV = occ2 ? 64 : (M >= 128 ? 128 : round16(M));
     a.nblk = cdiv(M, a.BKV);
+    a.tmem_cols = occ2 ? 256 : 512;
     CUtensorMap mQ, mK, mV, mdO;
     if (int e = make_head_map(&mQ, Q, dh, H, N, B, ldq, q_bs, 128)) return e;
     if (int e = make_head_map(&mdO, dO, dh, H, N, B, lddo, do_bs, 128)) return e;
     if (int e = make_head_map(&mK, K, dh, H, M, B, ldk, k_bs, a.BKV)) return e;
     if (int e = make_head_map(&mV, V, dh, H, M, B, ldv, v_bs, a.BKV)) return e;
-    const size_t fixed = (size_t)2 * a.DC * 16384 + 32768 + 256 + 1024;
+    const size_t fixed = (size_t)2 * a.DC * 16384 + (size_t)cdiv(a.BKV, 64) * 16384 + 256 + 1024;
     const size_t per_stage = (size_t)2 * a.DC * a.BKV * 128;
-    a.kst = (fixed + 2 * per_stage <= 227 * 1024 && a.nblk > 1) ? 2 : 1;
+    const size_t cap = (size_t)(occ2 ? 113 : 227) * 1024;
+    a.kst = (fixed + 2 * per_stage <= cap && a.nblk > 1) ? 2 : 1;
     const size_t smem = fixed + a.kst * per_stage;
-    E4T_CHECK(smem <= 227 * 1024, "e4t_attn_bwd(dQ): smem budget exceeded (%zu)", smem);
-    if (attn_cg(1) == 4) attn_bwd_dq_kernel<4><<<dim3(cdiv(N, 128), H, B), 128 + 128 * 4, smem, st>>>(mQ, mK, mV, mdO, a);
-    else attn_bwd_dq_kernel<2><<<dim3(cdiv(N, 128), H, B), 128 + 128 * 2, smem, st>>>(mQ, mK, mV, mdO, a);
+    E4T_CHECK(smem <= cap, "e4t_attn_bwd(dQ): smem budget exceeded (%zu)", smem);
+    if (occ2) attn_bwd_dq_kernel<2, 2><<<dim3(cdiv(N, 128), H, B), 128 + 128 * 2, smem, st>>>(mQ, mK, mV, mdO, a);
+    else if (attn_cg(1) == 4) attn_bwd_dq_kernel<4, 1><<<dim3(cdiv(N, 128), H, B), 128 + 128 * 4, smem, st>>>(mQ, mK, mV, mdO, a);
+    else attn_bwd_dq_kernel<2, 1><<<dim3(cdiv(N, 128), H, B), 128 + 128 * 2, smem, st>>>(mQ, mK, mV, mdO, a);
     E4T_COUNT_LAUNCH();
     E4T_LAUNCH_CHECK();
   }
   {  // dK, dV
-    const int bq_max = a.dpad > 128 ? 64 : 128;
+    const bool occ2 = (a.DC == 1 && N >= 512 && attn_cg(3) != 0);   // two CTAs/SM: 64-wide query blocks
+    const int bq_max = (a.dpad > 128 || occ2) ? 64 : 128;
     a.BKV = N >= bq_max ? bq_max : round16(N);
     a.nblk = cdiv(N, a.BKV);
+    a.tmem_cols = occ2 ? 256 : 512;
     CUtensorMap mQ, mK, mV, mdO;
     if (int e = make_head_map(&mQ, Q, dh, H, N, B, ldq, q_bs, a.BKV)) return e;
     if (int e = make_head_map(&mdO, dO, dh, H, N, B, lddo, do_bs, a.BKV)) return e;
     if (int e = make_head_map(&mK, K, dh, H, M, B, ldk, k_bs, 128)) return e;
     if (int e = make_head_map(&mV, V, dh, H, M, B, ldv, v_bs, 128)) return e;
-    const size_t fixed = (size_t)2 * a.DC * 16384 + 65536 + 1024 + 256 + 1024;
+    const size_t fixed = (size_t)2 * a.DC * 16384 + (size_t)2 * cdiv(a.BKV, 64) * 16384 + 1024 + 256 + 1024;
     const size_t per_stage = (size_t)2 * a.DC * a.BKV * 128;
-    a.kst = (fixed + 2 * per_stage <= 227 * 1024 && a.nblk > 1) ? 2 : 1;
+    const size_t cap = (size_t)(occ2 ? 113 : 227) * 1024;
+    a.kst = (fixed + 2 * per_stage <= cap && a.nblk > 1) ? 2 : 1;
     const size_t smem = fixed + a.kst * per_stage;
-    E4T_CHECK(smem <= 227 * 1024, "e4t_attn_bwd(dKV): smem budget exceeded (%zu)", smem);
-    if (attn_cg(2) == 4) attn_bwd_dkv_kernel<4><<<dim3(cdiv(M, 128), H, B), 128 + 128 * 4, smem, st>>>(mQ, mK, mV, mdO, a);
-    else attn_bwd_dkv_kernel<2><<<dim3(cdiv(M, 128), H, B), 128 + 128 * 2, smem, st>>>(mQ, mK, mV, mdO, a);
+    E4T_CHECK(smem <= cap, "e4t_attn_bwd(dKV): smem budget exceeded (%zu)", smem);
+    if (occ2) attn_bwd_dkv_kernel<2, 2><<<dim3(cdiv(M, 128), H, B), 128 + 128 * 2, smem, st>>>(mQ, mK, mV, mdO, a);
+    else if (attn_cg(2) == 4) attn_bwd_dkv_kernel<4, 1><<<dim3(cdiv(M, 128), H, B), 128 + 128 * 4, smem, st>>>(mQ, mK, mV, mdO, a);
+    else attn_bwd_dkv_kernel<2, 1><<<dim3(cdiv(M, 128), H, B), 128 + 128 * 2, smem, st>>>(mQ, mK, mV, mdO, a);
     E4T_COUNT_LAUNCH();
     E4T_LAUNCH_CHECK();
   }
