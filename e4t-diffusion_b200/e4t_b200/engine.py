@@ -29,6 +29,21 @@ def add_noise(latents, noise, timesteps, acp):
     return a.view(-1, 1, 1, 1) * latents + s.view(-1, 1, 1, 1) * noise
 
 
+def all_reduce_sum_(flat, group=None):
+    """Data-parallel exchange of a flat gradient arena: ONE all-reduce(SUM) (NCCL over NVLink/NVSwitch on GPUs,
+    gloo in the CPU tests).  Returns the scale (1/world) that turns the sum into the DDP average; FlatAdamW folds it
+    into the optimiser kernel instead of spending another pass over the arena."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        return 1.0 / dist.get_world_size(group)
+    return 1.0
+
+
+def shard_seed(base_seed, rank):
+    """Per-rank data seed (the batch shards over images; ranks never exchange activations)."""
+    return base_seed + 1000 * rank
+
+
 class FlatAdamW:
     """torch.optim.AdamW semantics over a flat arena (amsgrad=False).  `params`: iterable of nn.Parameter."""
 
@@ -84,10 +99,7 @@ class FlatAdamW:
     def all_reduce_grads(self):
         """Data-parallel gradient exchange: one NCCL all-reduce (SUM) of the gradient arena; the 1/world average
         is folded into the optimiser kernel's grad_scale."""
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.process_group) > 1:
-            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.process_group)
-            return 1.0 / dist.get_world_size(self.process_group)
-        return 1.0
+        return all_reduce_sum_(self.grad, self.process_group)
 
     def step(self, grad_scale=1.0):
         self.step_count += 1
