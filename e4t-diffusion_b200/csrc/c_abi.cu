@@ -26,7 +26,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 static PFN_encodeTiled g_encode = nullptr;
 
 int e4t_tmap_encode(CUtensorMap* map, const void* gptr, int rank, const uint64_t* dims,
-                    const uint64_t* strides_bytes, const uint32_t* box, int elem_bytes) {
+                    const uint64_t* strides_bytes, const uint32_t* box, int elem_bytes, int swizzle_bytes) {
   if (!g_encode) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -45,7 +45,11 @@ int e4t_tmap_encode(CUtensorMap* map, const void* gptr, int rank, const uint64_t
   }
   CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   CUresult r = g_encode(map, dt, (cuuint32_t)rank, const_cast<void*>(gptr), gdim, gstr, bdim, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                        : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                        : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     return e4t_set_error(

@@ -14,6 +14,7 @@
 // {A 128x64, B BNx64} bf16 tiles (SWIZZLE_128B), two TMEM accumulator stages of 256 columns so the epilogue of
 // tile i overlaps the MMAs of tile i+1.
 #include "common.cuh"
+#include <stdlib.h>
 
 struct GemmArgs {
   int M, N, K, batch;
@@ -31,22 +32,26 @@ struct GemmArgs {
   const bf16* residual;  // [M][ldr] bf16 or null
   long long ldr, res_bstride;
   float alpha;
+  int debug;      // E4T_GEMM_DEBUG bit0: skip epilogue body; bit1: skip tmem loads only
+  int tma_store;  // bf16 output through smem staging + TMA store (coalesced, asynchronous)
 };
 
 static constexpr int kBM = 128;
 static constexpr int kBK = 64;
 static constexpr int kATileBytes = kBM * kBK * 2;  // 16 KiB
 static constexpr int kThreads = 256;
+static constexpr int kCSlabs = 4;  // output staging slabs (8 KiB each) for the TMA-store epilogue
 
 __global__ void __launch_bounds__(kThreads, 1)
 e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                const GemmArgs g) {
+                const __grid_constant__ CUtensorMap mapC, const GemmArgs g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // align dynamic smem to 1024 B (SWIZZLE_128B atoms)
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int b_tile_bytes = g.BN * kBK * 2;
   const int stage_bytes = kATileBytes + b_tile_bytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)g.stages * stage_bytes);
+  uint8_t* stage_c = smem + (size_t)g.stages * stage_bytes;  // 2 x [128 rows][64 B] output slabs (SWIZZLE_64B)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_c + kCSlabs * 8192);
   uint64_t* empty_bar = full_bar + g.stages;
   uint64_t* tfull_bar = empty_bar + g.stages;
   uint64_t* tempty_bar = tfull_bar + 2;
@@ -58,6 +63,7 @@ e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA);
     tma_prefetch_desc(&mapB);
+    if (g.tma_store) tma_prefetch_desc(&mapC);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < g.stages; ++i) {
@@ -173,6 +179,7 @@ e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     const int row = ew * 32 + lane;
     int as = 0;
     uint32_t aph = 0;
+    uint32_t slab_ctr = 0;
     for (long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int n_t = (int)(t % g.n_tiles);
       long r = t / g.n_tiles;
@@ -188,6 +195,71 @@ e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       const float* rg = (g.rowgroup && row_ok) ? g.rowgroup + (long long)(m / g.rows_per_group) * g.N : nullptr;
       const bf16* res = (g.residual && row_ok) ? g.residual + (long long)bz * g.res_bstride + (long long)m * g.ldr
                                                : nullptr;
+      if (g.debug & 1) {
+      } else if (g.tma_store) {
+        // ---- bf16 output: registers -> swizzled smem slab -> TMA store (full-line coalesced writes) ----
+        const bool leader = threadIdx.x == 128;
+        const uint32_t sw = ((uint32_t)row >> 1) & 3u;
+        for (int c = 0; c < g.BN && n0 + c < g.N; c += 32) {
+          uint32_t v[32];
+          __syncwarp();
+          if (!(g.debug & 2)) {
+            tmem_ld32(t_row + (uint32_t)c, v);
+            tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = 0;
+          }
+          uint32_t w[16];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int n = n0 + c + q * 8;
+            float f[8];
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) f[jj] = __uint_as_float(v[q * 8 + jj]) * g.alpha;
+            if (n + 8 <= g.N) {
+              if (g.bias) {
+                const float4 b0 = *reinterpret_cast<const float4*>(g.bias + n);
+                const float4 b1 = *reinterpret_cast<const float4*>(g.bias + n + 4);
+                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+              }
+              if (rg) {
+                const float4 b0 = *reinterpret_cast<const float4*>(rg + n);
+                const float4 b1 = *reinterpret_cast<const float4*>(rg + n + 4);
+                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
+                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
+              }
+              if (res) {
+                const uint4 rv = *reinterpret_cast<const uint4*>(res + n);
+                const float2 r0 = unpack_bf16(rv.x), r1 = unpack_bf16(rv.y), r2 = unpack_bf16(rv.z),
+                             r3 = unpack_bf16(rv.w);
+                f[0] += r0.x; f[1] += r0.y; f[2] += r1.x; f[3] += r1.y;
+                f[4] += r2.x; f[5] += r2.y; f[6] += r3.x; f[7] += r3.y;
+              }
+            }
+            w[q * 4 + 0] = pack_bf16(f[0], f[1]);
+            w[q * 4 + 1] = pack_bf16(f[2], f[3]);
+            w[q * 4 + 2] = pack_bf16(f[4], f[5]);
+            w[q * 4 + 3] = pack_bf16(f[6], f[7]);
+          }
+          uint8_t* slab = stage_c + (slab_ctr & (kCSlabs - 1)) * 8192;
+          if (g.debug & 4) continue;
+          if (leader) tma_store_wait_read<kCSlabs - 1>();  // the store that last read this slab has drained
+          asm volatile("bar.sync 3, 128;" ::: "memory");
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<uint4*>(slab + row * 64 + ((((uint32_t)q) ^ sw) << 4)) =
+                make_uint4(w[q * 4], w[q * 4 + 1], w[q * 4 + 2], w[q * 4 + 3]);
+          fence_proxy_async_smem();
+          asm volatile("bar.sync 4, 128;" ::: "memory");
+          if (leader) {
+            tma_store_3d(&mapC, slab, n0 + c, m_t * kBM, bz);
+            tma_store_commit();
+          }
+          ++slab_ctr;
+        }
+      } else
       for (int c = 0; c < g.BN; c += 32) {
         uint32_t v[32];
         __syncwarp();
@@ -257,6 +329,7 @@ e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       as ^= 1;
       if (as == 0) aph ^= 1u;
     }
+    if (g.tma_store && threadIdx.x == 128) tma_store_wait_all();  // smem must outlive the bulk stores
   }
 
   tc_fence_before();
@@ -281,24 +354,28 @@ static int num_sms() {
   return g_num_sms;
 }
 
-static int pick_bn(int N, long m_tiles_x_batch, bool b_mn, int force_bn) {
+// Tile-width choice by a small cost model (cycles per SM):
+//   per 64-deep k-chunk a CTA needs max(MMA, smem operand reads) = max(2*BN, 128+BN) cycles
+//   (tcgen05 128xBNx16 = BN/2 cycles, 4 per chunk; smem feeds (128+BN)*128 B per chunk at 128 B/cycle);
+//   the epilogue of a tile overlaps the next tile's mainloop, so a tile costs max(mainloop, epilogue) plus a fixed
+//   pipeline bubble; the persistent grid runs ceil(tiles / SMs) rounds.
+static int pick_bn(int N, long m_tiles_x_batch, bool b_mn, int force_bn, int kchunks_per_tile = 16) {
   if (force_bn > 0) return force_bn;
   const int step = b_mn ? 64 : 32;
   int best = 0;
-  double best_score = -1.0;
+  double best_cost = 1e30;
+  const double sms = (double)num_sms();
   for (int bn = 256; bn >= 64; bn -= step) {
     const int tiles_n = cdiv(N, bn);
-    const double eff = (double)N / ((double)tiles_n * bn);
     const double tiles = (double)tiles_n * (double)m_tiles_x_batch;
-    const double sms = (double)num_sms();
-    // wave efficiency of a persistent launch
-    const double waves = tiles / sms;
-    const double wave_eff = waves / (double)((long)((tiles + sms - 1) / sms));
-    // wider tiles are a little cheaper per flop (A-tile reuse); tiny preference
-    const double width = 0.9 + 0.1 * bn / 256.0;
-    const double score = eff * wave_eff * width;
-    if (score > best_score + 1e-9) {
-      best_score = score;
+    const double chunk = (2.0 * bn > 128.0 + bn) ? 2.0 * bn : 128.0 + bn;
+    const double mainloop = kchunks_per_tile * chunk;
+    const double epilogue = 250.0 + 6.0 * bn;
+    const double tile = (mainloop > epilogue ? mainloop : epilogue) + 150.0;
+    const double rounds = (double)((long)((tiles + sms - 1) / sms));
+    const double cost = rounds * tile + epilogue;
+    if (cost < best_cost - 1e-6) {
+      best_cost = cost;
       best = bn;
     }
   }
@@ -306,12 +383,33 @@ static int pick_bn(int N, long m_tiles_x_batch, bool b_mn, int force_bn) {
 }
 
 static int launch_gemm(const CUtensorMap& mA, const CUtensorMap& mB, GemmArgs& g, cudaStream_t stream) {
+  // output map for the TMA-store epilogue: bf16 [batch][M][N], box 32 cols x 128 rows, SWIZZLE_64B
+  CUtensorMap mC;
+  memset(&mC, 0, sizeof(mC));
+  g.tma_store = 0;
+  {
+    const char* d = getenv("E4T_GEMM_DEBUG");
+    g.debug = d ? atoi(d) : 0;
+  }
+  static int use_tma_store = -1;
+  if (use_tma_store < 0) {
+    const char* e = getenv("E4T_GEMM_TMA_STORE");
+    use_tma_store = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (use_tma_store && g.out_mode == 0 && (g.N % 8) == 0 && (g.ldo % 8) == 0 && ((uintptr_t)g.out % 16) == 0 &&
+      (g.batch == 1 || (g.out_bstride % 8) == 0)) {
+    uint64_t dims[3] = {(uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.batch};
+    uint64_t str[2] = {(uint64_t)g.ldo * 2, (uint64_t)(g.batch > 1 ? g.out_bstride : (long long)g.M * g.ldo) * 2};
+    uint32_t box[3] = {32, kBM, 1};
+    if (int e = e4t_tmap_encode(&mC, g.out, 3, dims, str, box, 2, 64)) return e;
+    g.tma_store = 1;
+  }
   const int stage_bytes = kATileBytes + g.BN * kBK * 2;
-  int stages = (196 * 1024) / stage_bytes;
+  int stages = (192 * 1024) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages > g.kper) stages = g.kper < 2 ? 2 : g.kper;
   g.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 4) * sizeof(uint64_t) + 16 + 1024;
+  const size_t smem = (size_t)stages * stage_bytes + kCSlabs * 8192 + (2 * stages + 4) * sizeof(uint64_t) + 16 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     E4T_CUDA(cudaFuncSetAttribute(e4t_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -320,7 +418,7 @@ static int launch_gemm(const CUtensorMap& mA, const CUtensorMap& mB, GemmArgs& g
   const long total = (long)g.batch * g.splits * g.m_tiles * g.n_tiles;
   int grid = (int)(total < num_sms() ? total : num_sms());
   if (grid < 1) return 0;
-  e4t_gemm_kernel<<<grid, kThreads, smem, stream>>>(mA, mB, g);
+  e4t_gemm_kernel<<<grid, kThreads, smem, stream>>>(mA, mB, mC, g);
   E4T_COUNT_LAUNCH();
   E4T_LAUNCH_CHECK();
   return 0;
@@ -347,7 +445,7 @@ extern "C" int e4t_gemm_bf16(const void* A, const void* B, void* out, int M, int
   if (splits > g.kchunks) splits = g.kchunks;
   g.kper = cdiv(g.kchunks, splits);
   g.splits = cdiv(g.kchunks, g.kper);  // no empty split
-  g.BN = pick_bn(N, (long)g.m_tiles * batch * g.splits, b_mn != 0, force_bn);
+  g.BN = pick_bn(N, (long)g.m_tiles * batch * g.splits, b_mn != 0, force_bn, g.kper);
   E4T_CHECK(g.BN >= 32 && g.BN <= 256 && (g.BN % (b_mn ? 64 : 32)) == 0, "e4t_gemm_bf16: bad BN %d", g.BN);
   g.n_tiles = cdiv(N, g.BN);
   E4T_CHECK(g.splits == 1 || out_mode == 2, "e4t_gemm_bf16: split-K requires atomic fp32 output");
@@ -417,7 +515,7 @@ extern "C" int e4t_conv3x3_bf16(const void* x, const void* w, void* out, int B, 
   g.m_tiles = cdiv(g.M, kBM);
   g.kchunks = 9 * g.cin_chunks;
   g.kper = g.kchunks; g.splits = 1;
-  g.BN = pick_bn(Cout, g.m_tiles, false, force_bn);
+  g.BN = pick_bn(Cout, g.m_tiles, false, force_bn, g.kchunks);
   g.n_tiles = cdiv(Cout, g.BN);
   g.out = out; g.out_mode = out_mode; g.ldo = Cout; g.out_bstride = 0;
   g.bias = bias; g.rowgroup = rowgroup; g.rows_per_group = img;
