@@ -39,7 +39,7 @@ struct GemmArgs {
 static constexpr int kBM = 128;
 static constexpr int kBK = 64;
 static constexpr int kATileBytes = kBM * kBK * 2;  // 16 KiB
-static constexpr int kThreads = 256;
+static constexpr int kThreads = 384;  // 4 role warps + 8 epilogue warps (2 column halves x 4 lane quadrants)
 static constexpr int kCSlabs = 4;  // output staging slabs (8 KiB each) for the TMA-store epilogue
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -72,7 +72,7 @@ e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 128);
+      mbar_init(&tempty_bar[i], 256);
     }
     fence_mbar_init();
   }
@@ -174,8 +174,10 @@ e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue (128 threads, one accumulator row each) =====================
-    const int ew = warp - 4;  // == warp % 4 -> TMEM lane quadrant
+    // ===================== epilogue (256 threads: one accumulator row each, two column halves) ==============
+    // warp (4 + 4*half + e) owns TMEM lanes [32e, 32e+32) and the 32-column slabs with (slab & 1) == half.
+    const int ew = (warp - 4) & 3;   // == warp % 4 -> TMEM lane quadrant
+    const int half = (warp - 4) >> 2;
     const int row = ew * 32 + lane;
     int as = 0;
     uint32_t aph = 0;
@@ -198,18 +200,17 @@ e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       if (g.debug & 1) {
       } else if (g.tma_store) {
         // ---- bf16 output: registers -> swizzled smem slab -> TMA store (full-line coalesced writes) ----
-        const bool leader = threadIdx.x == 128;
+        const bool leader = (threadIdx.x == 128 + 128 * half);
         const uint32_t sw = ((uint32_t)row >> 1) & 3u;
-        for (int c = 0; c < g.BN && n0 + c < g.N; c += 32) {
-          uint32_t v[32];
+        uint32_t v[32];
+        int c = 32 * half;
+        const bool any = (c < g.BN && n0 + c < g.N);
+        if (any) {
           __syncwarp();
-          if (!(g.debug & 2)) {
-            tmem_ld32(t_row + (uint32_t)c, v);
-            tmem_ld_wait();
-          } else {
-#pragma unroll
-            for (int e = 0; e < 32; ++e) v[e] = 0;
-          }
+          tmem_ld32(t_row + (uint32_t)c, v);
+        }
+        for (; c < g.BN && n0 + c < g.N; c += 64) {
+          tmem_ld_wait();
           uint32_t w[16];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -243,16 +244,25 @@ e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             w[q * 4 + 2] = pack_bf16(f[4], f[5]);
             w[q * 4 + 3] = pack_bf16(f[6], f[7]);
           }
-          uint8_t* slab = stage_c + (slab_ctr & (kCSlabs - 1)) * 8192;
+          // prefetch the next slab of this half while the current one is staged and stored
+          const int cn = c + 64;
+          if (cn < g.BN && n0 + cn < g.N) {
+            __syncwarp();
+            tmem_ld32(t_row + (uint32_t)cn, v);
+          }
           if (g.debug & 4) continue;
-          if (leader) tma_store_wait_read<kCSlabs - 1>();  // the store that last read this slab has drained
-          asm volatile("bar.sync 3, 128;" ::: "memory");
+          // this half cycles through staging slabs {half, half + 2}
+          uint8_t* slab = stage_c + (half + 2 * (slab_ctr & 1)) * 8192;
+          if (leader) tma_store_wait_read<1>();  // the store that last read this slab has drained
+          if (half == 0) asm volatile("bar.sync 3, 128;" ::: "memory");
+          else asm volatile("bar.sync 5, 128;" ::: "memory");
 #pragma unroll
           for (int q = 0; q < 4; ++q)
             *reinterpret_cast<uint4*>(slab + row * 64 + ((((uint32_t)q) ^ sw) << 4)) =
                 make_uint4(w[q * 4], w[q * 4 + 1], w[q * 4 + 2], w[q * 4 + 3]);
           fence_proxy_async_smem();
-          asm volatile("bar.sync 4, 128;" ::: "memory");
+          if (half == 0) asm volatile("bar.sync 4, 128;" ::: "memory");
+          else asm volatile("bar.sync 6, 128;" ::: "memory");
           if (leader) {
             tma_store_3d(&mapC, slab, n0 + c, m_t * kBM, bz);
             tma_store_commit();
@@ -260,7 +270,7 @@ e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
           ++slab_ctr;
         }
       } else
-      for (int c = 0; c < g.BN; c += 32) {
+      for (int c = 32 * half; c < g.BN; c += 64) {
         uint32_t v[32];
         __syncwarp();
         tmem_ld32(t_row + (uint32_t)c, v);
@@ -329,7 +339,7 @@ e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       as ^= 1;
       if (as == 0) aph ^= 1u;
     }
-    if (g.tma_store && threadIdx.x == 128) tma_store_wait_all();  // smem must outlive the bulk stores
+    if (g.tma_store && (threadIdx.x == 128 || threadIdx.x == 256)) tma_store_wait_all();  // smem must outlive the stores
   }
 
   tc_fence_before();

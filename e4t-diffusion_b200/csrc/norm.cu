@@ -10,92 +10,100 @@
 // mode 0: plain stats of x.
 // mode 1: backward stats: (sum dxhat, sum dxhat*xhat) with dxhat = dy * act'(y0) * gamma.
 // ---------------------------------------------------------------------------------------------
-static constexpr int kGNThreads = 256;
-static constexpr int kGNMaxPairs = 6;  // C <= 3072
+// Thread mapping (all four kernels): a thread owns ONE 8-channel vector column (16-byte loads, coalesced across
+// the warp) and walks rows; its per-channel constants live in registers.  blockDim = vpr * k (vpr = C/8 vector
+// columns, k = rows handled concurrently by one CTA), so no thread is idle and no per-element smem lookups occur.
+static constexpr int kGNMaxThreads = 320;
 
 struct GNChan {
   float mean, rstd, gamma, beta;
 };
 
-__device__ __forceinline__ void gn_load_chan(GNChan* sc, const float* __restrict__ stats, const float* __restrict__ gamma,
-                                              const float* __restrict__ beta, int b, int C, int G, float inv_n,
-                                              float eps) {
-  const int cpg = C / G;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = c / cpg;
-    const float s = stats[((long)b * G + g) * 2], ss = stats[((long)b * G + g) * 2 + 1];
-    const float mean = s * inv_n;
-    const float var = fmaxf(ss * inv_n - mean * mean, 0.f);
-    GNChan ch;
-    ch.mean = mean;
-    ch.rstd = rsqrtf(var + eps);
-    ch.gamma = gamma[c];
-    ch.beta = beta[c];
-    sc[c] = ch;
-  }
-}
-
 __device__ __forceinline__ float silu_grad(float y) {
   const float sg = 1.f / (1.f + __expf(-y));
   return sg * (1.f + y * (1.f - sg));
 }
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  return make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+}
+// per-channel (mean, rstd, gamma, beta) of this thread's 8 channels, from the forward sums
+__device__ __forceinline__ void gn_thread_chan(GNChan* ch, const float* __restrict__ stats,
+                                               const float* __restrict__ gamma, const float* __restrict__ beta, int b,
+                                               int c0, int C, int G, float inv_n, float eps) {
+  const int cpg = C / G;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int g = (c0 + j) / cpg;
+    const float s = stats[((long)b * G + g) * 2], ss = stats[((long)b * G + g) * 2 + 1];
+    const float mean = s * inv_n;
+    ch[j].mean = mean;
+    ch[j].rstd = rsqrtf(fmaxf(ss * inv_n - mean * mean, 0.f) + eps);
+    ch[j].gamma = gamma[c0 + j];
+    ch[j].beta = beta[c0 + j];
+  }
+}
 
+// sums[b][g] += (Σ a, Σ b) over this CTA's rows.  MODE 0: (x, x²).  MODE 1: (dxhat, dxhat·xhat).
 template <int MODE>
-__global__ void __launch_bounds__(kGNThreads)
+__global__ void __launch_bounds__(kGNMaxThreads)
 gn_stats_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, const float* __restrict__ fstats,
                 const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ sums, int HW,
                 int C, int G, int rows_per_cta, float eps, int act) {
   extern __shared__ __align__(16) uint8_t gsm[];
-  float2* spair = reinterpret_cast<float2*>(gsm);                               // [C/2]
-  GNChan* sc = reinterpret_cast<GNChan*>(gsm + (size_t)(C / 2) * sizeof(float2));  // [C] (MODE 1 only)
+  float2* schan = reinterpret_cast<float2*>(gsm);  // [C] per-channel partials
   const int b = blockIdx.y;
+  const int vpr = C / 8;
+  const int cv = threadIdx.x % vpr, rl = threadIdx.x / vpr, rstep = blockDim.x / vpr;
+  const int c0 = cv * 8;
   const int r0 = blockIdx.x * rows_per_cta;
   const int r1 = min(HW, r0 + rows_per_cta);
-  const int npairs = C / 2;
-  if (MODE == 1) {
-    gn_load_chan(sc, fstats, gamma, beta, b, C, G, 1.f / ((float)HW * (float)(C / G)), eps);
-    __syncthreads();
-  }
-  float a0[kGNMaxPairs], a1[kGNMaxPairs];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) schan[c] = make_float2(0.f, 0.f);
+  GNChan ch[8];
+  if (MODE == 1) gn_thread_chan(ch, fstats, gamma, beta, b, c0, C, G, 1.f / ((float)HW * (float)(C / G)), eps);
+  __syncthreads();
+  float a0[8], a1[8];
 #pragma unroll
-  for (int k = 0; k < kGNMaxPairs; ++k) a0[k] = a1[k] = 0.f;
-  const uint32_t* xp = reinterpret_cast<const uint32_t*>(x) + ((long)b * HW) * npairs;
-  const uint32_t* dp = MODE == 1 ? reinterpret_cast<const uint32_t*>(dy) + ((long)b * HW) * npairs : nullptr;
-  for (int r = r0; r < r1; ++r) {
+  for (int j = 0; j < 8; ++j) a0[j] = a1[j] = 0.f;
+  const bf16* xb = x + ((long)b * HW) * C + c0;
+  const bf16* db = MODE == 1 ? dy + ((long)b * HW) * C + c0 : nullptr;
+#pragma unroll 4
+  for (int r = r0 + rl; r < r1; r += rstep) {
+    float xv[8];
+    unpack8(*reinterpret_cast<const uint4*>(xb + (long)r * C), xv);
+    if (MODE == 0) {
 #pragma unroll
-    for (int k = 0; k < kGNMaxPairs; ++k) {
-      const int cp = threadIdx.x + k * kGNThreads;
-      if (cp < npairs) {
-        const float2 v = unpack_bf16(xp[(long)r * npairs + cp]);
-        if (MODE == 0) {
-          a0[k] += v.x + v.y;
-          a1[k] += v.x * v.x + v.y * v.y;
-        } else {
-          const float2 d = unpack_bf16(dp[(long)r * npairs + cp]);
-          const GNChan c0 = sc[2 * cp], c1 = sc[2 * cp + 1];
-          const float xh0 = (v.x - c0.mean) * c0.rstd, xh1 = (v.y - c1.mean) * c1.rstd;
-          float g0 = d.x * c0.gamma, g1 = d.y * c1.gamma;
-          if (act) {
-            g0 *= silu_grad(xh0 * c0.gamma + c0.beta);
-            g1 *= silu_grad(xh1 * c1.gamma + c1.beta);
-          }
-          a0[k] += g0 + g1;
-          a1[k] += g0 * xh0 + g1 * xh1;
-        }
+      for (int j = 0; j < 8; ++j) {
+        a0[j] += xv[j];
+        a1[j] += xv[j] * xv[j];
+      }
+    } else {
+      float dv[8];
+      unpack8(*reinterpret_cast<const uint4*>(db + (long)r * C), dv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (xv[j] - ch[j].mean) * ch[j].rstd;
+        float g = dv[j] * ch[j].gamma;
+        if (act) g *= silu_grad(xh * ch[j].gamma + ch[j].beta);
+        a0[j] += g;
+        a1[j] += g * xh;
       }
     }
   }
 #pragma unroll
-  for (int k = 0; k < kGNMaxPairs; ++k) {
-    const int cp = threadIdx.x + k * kGNThreads;
-    if (cp < npairs) spair[cp] = make_float2(a0[k], a1[k]);
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(&schan[c0 + j].x, a0[j]);
+    atomicAdd(&schan[c0 + j].y, a1[j]);
   }
   __syncthreads();
-  const int ppg = (C / G) / 2;  // pairs per group
+  const int cpg = C / G;
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
     float s = 0.f, ss = 0.f;
-    for (int i = 0; i < ppg; ++i) {
-      const float2 p = spair[g * ppg + i];
+    for (int i = 0; i < cpg; ++i) {
+      const float2 p = schan[g * cpg + i];
       s += p.x;
       ss += p.y;
     }
@@ -106,87 +114,85 @@ gn_stats_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, const f
 
 // MODE 0: y = act(xhat*gamma+beta).   MODE 1: dx = rstd*(dxhat - mean(dxhat) - xhat*mean(dxhat*xhat)).
 template <int MODE>
-__global__ void __launch_bounds__(kGNThreads)
+__global__ void __launch_bounds__(kGNMaxThreads)
 gn_apply_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, const float* __restrict__ fstats,
                 const float* __restrict__ bstats, const float* __restrict__ gamma, const float* __restrict__ beta,
                 bf16* __restrict__ out, int HW, int C, int G, int rows_per_cta, float eps, int act) {
-  extern __shared__ __align__(16) uint8_t gsm[];
-  GNChan* sc = reinterpret_cast<GNChan*>(gsm);               // [C]
-  float2* sb = reinterpret_cast<float2*>(sc + C);            // [G] backward means (MODE 1)
   const int b = blockIdx.y;
   const float inv_n = 1.f / ((float)HW * (float)(C / G));
-  gn_load_chan(sc, fstats, gamma, beta, b, C, G, inv_n, eps);
-  if (MODE == 1) {
-    for (int g = threadIdx.x; g < G; g += blockDim.x)
-      sb[g] = make_float2(bstats[((long)b * G + g) * 2] * inv_n, bstats[((long)b * G + g) * 2 + 1] * inv_n);
-  }
-  __syncthreads();
+  const int vpr = C / 8;
+  const int cv = threadIdx.x % vpr, rl = threadIdx.x / vpr, rstep = blockDim.x / vpr;
+  const int c0 = cv * 8;
+  GNChan ch[8];
+  gn_thread_chan(ch, fstats, gamma, beta, b, c0, C, G, inv_n, eps);
+  float scale[8], shift[8], m1[8], m2[8];
   const int cpg = C / G;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    scale[j] = ch[j].rstd * ch[j].gamma;
+    shift[j] = ch[j].beta - ch[j].mean * scale[j];
+    if (MODE == 1) {
+      const int g = (c0 + j) / cpg;
+      m1[j] = bstats[((long)b * G + g) * 2] * inv_n;
+      m2[j] = bstats[((long)b * G + g) * 2 + 1] * inv_n;
+    }
+  }
   const int r0 = blockIdx.x * rows_per_cta;
   const int r1 = min(HW, r0 + rows_per_cta);
-  const int vec_per_row = C / 8;
-  const long base = ((long)b * HW + r0) * C;
-  const int nvec = (r1 - r0) * vec_per_row;
-  for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
-    const int c0 = (i % vec_per_row) * 8;
-    const uint4 xv = *reinterpret_cast<const uint4*>(x + base + (long)i * 8);
-    uint4 dv = make_uint4(0, 0, 0, 0);
-    if (MODE == 1) dv = *reinterpret_cast<const uint4*>(dy + base + (long)i * 8);
-    const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w};
-    const uint32_t ds[4] = {dv.x, dv.y, dv.z, dv.w};
-    uint32_t os[4];
+  const long base = ((long)b * HW) * C + c0;
+#pragma unroll 4
+  for (int r = r0 + rl; r < r1; r += rstep) {
+    float xv[8], o[8];
+    unpack8(*reinterpret_cast<const uint4*>(x + base + (long)r * C), xv);
+    if (MODE == 0) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 v = unpack_bf16(xs[j]);
-      const GNChan ca = sc[c0 + 2 * j], cb = sc[c0 + 2 * j + 1];
-      const float xh0 = (v.x - ca.mean) * ca.rstd, xh1 = (v.y - cb.mean) * cb.rstd;
-      float o0, o1;
-      if (MODE == 0) {
-        o0 = xh0 * ca.gamma + ca.beta;
-        o1 = xh1 * cb.gamma + cb.beta;
-        if (act) {
-          o0 = silu_f(o0);
-          o1 = silu_f(o1);
-        }
-      } else {
-        const float2 d = unpack_bf16(ds[j]);
-        float g0 = d.x * ca.gamma, g1 = d.y * cb.gamma;
-        if (act) {
-          g0 *= silu_grad(xh0 * ca.gamma + ca.beta);
-          g1 *= silu_grad(xh1 * cb.gamma + cb.beta);
-        }
-        const float2 ma = sb[(c0 + 2 * j) / cpg], mb = sb[(c0 + 2 * j + 1) / cpg];
-        o0 = ca.rstd * (g0 - ma.x - xh0 * ma.y);
-        o1 = cb.rstd * (g1 - mb.x - xh1 * mb.y);
+      for (int j = 0; j < 8; ++j) {
+        o[j] = fmaf(xv[j], scale[j], shift[j]);
+        if (act) o[j] = silu_f(o[j]);
       }
-      os[j] = pack_bf16(o0, o1);
+    } else {
+      float dv[8];
+      unpack8(*reinterpret_cast<const uint4*>(dy + base + (long)r * C), dv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (xv[j] - ch[j].mean) * ch[j].rstd;
+        float g = dv[j] * ch[j].gamma;
+        if (act) g *= silu_grad(fmaf(xv[j], scale[j], shift[j]));
+        o[j] = ch[j].rstd * (g - m1[j] - xh * m2[j]);
+      }
     }
-    *reinterpret_cast<uint4*>(out + base + (long)i * 8) = make_uint4(os[0], os[1], os[2], os[3]);
+    *reinterpret_cast<uint4*>(out + base + (long)r * C) = pack8(o);
   }
 }
 
 static int gn_rows_per_cta(int B, int HW) {
   // aim for >= ~8 CTAs per SM overall
-  int rows = 32;
-  while (rows > 1 && (long)B * cdiv(HW, rows) < 148 * 8) rows >>= 1;
+  int rows = 64;
+  while (rows > 4 && (long)B * cdiv(HW, rows) < 148 * 8) rows >>= 1;
   return rows;
+}
+static int gn_block(int C) {
+  const int vpr = C / 8;
+  int k = 256 / vpr;
+  if (k < 1) k = 1;
+  return vpr * k;
 }
 
 // stats: fp32 [B][G][2] = (sum, sumsq); written by this call.
 extern "C" int e4t_groupnorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* stats, int B,
                                  int HW, int C, int G, float eps, int act_silu, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
-  E4T_CHECK(C % G == 0 && (C / G) % 2 == 0 && C % 8 == 0 && C <= 2 * kGNThreads * kGNMaxPairs,
-            "e4t_groupnorm_fwd: unsupported C=%d G=%d", C, G);
+  E4T_CHECK(C % G == 0 && C % 8 == 0 && C / 8 <= kGNMaxThreads, "e4t_groupnorm_fwd: unsupported C=%d G=%d", C, G);
   E4T_CUDA(cudaMemsetAsync(stats, 0, (size_t)B * G * 2 * sizeof(float), st));
   const int rows = gn_rows_per_cta(B, HW);
+  const int threads = gn_block(C);
   dim3 grid(cdiv(HW, rows), B);
-  gn_stats_kernel<0><<<grid, kGNThreads, (size_t)(C / 2) * sizeof(float2), st>>>(
-      (const bf16*)x, nullptr, nullptr, nullptr, nullptr, stats, HW, C, G, rows, eps, 0);
+  gn_stats_kernel<0><<<grid, threads, (size_t)C * sizeof(float2), st>>>((const bf16*)x, nullptr, nullptr, nullptr,
+                                                                        nullptr, stats, HW, C, G, rows, eps, 0);
   E4T_COUNT_LAUNCH();
   E4T_LAUNCH_CHECK();
-  gn_apply_kernel<0><<<grid, kGNThreads, (size_t)C * sizeof(GNChan), st>>>(
-      (const bf16*)x, nullptr, stats, nullptr, gamma, beta, (bf16*)y, HW, C, G, rows, eps, act_silu);
+  gn_apply_kernel<0><<<grid, threads, 0, st>>>((const bf16*)x, nullptr, stats, nullptr, gamma, beta, (bf16*)y, HW, C, G,
+                                               rows, eps, act_silu);
   E4T_COUNT_LAUNCH();
   E4T_LAUNCH_CHECK();
   return 0;
@@ -197,23 +203,17 @@ extern "C" int e4t_groupnorm_bwd(const void* x, const void* dy, const float* gam
                                  const float* stats, void* dx, float* scratch, int B, int HW, int C, int G, float eps,
                                  int act_silu, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
-  E4T_CHECK(C % G == 0 && (C / G) % 2 == 0 && C % 8 == 0 && C <= 2 * kGNThreads * kGNMaxPairs,
-            "e4t_groupnorm_bwd: unsupported C=%d G=%d", C, G);
+  E4T_CHECK(C % G == 0 && C % 8 == 0 && C / 8 <= kGNMaxThreads, "e4t_groupnorm_bwd: unsupported C=%d G=%d", C, G);
   E4T_CUDA(cudaMemsetAsync(scratch, 0, (size_t)B * G * 2 * sizeof(float), st));
-  static bool attr_set = false;
-  if (!attr_set) {
-    E4T_CUDA(cudaFuncSetAttribute(gn_stats_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    E4T_CUDA(cudaFuncSetAttribute(gn_apply_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    attr_set = true;
-  }
   const int rows = gn_rows_per_cta(B, HW);
+  const int threads = gn_block(C);
   dim3 grid(cdiv(HW, rows), B);
-  gn_stats_kernel<1><<<grid, kGNThreads, (size_t)(C / 2) * sizeof(float2) + (size_t)C * sizeof(GNChan), st>>>(
-      (const bf16*)x, (const bf16*)dy, stats, gamma, beta, scratch, HW, C, G, rows, eps, act_silu);
+  gn_stats_kernel<1><<<grid, threads, (size_t)C * sizeof(float2), st>>>((const bf16*)x, (const bf16*)dy, stats, gamma,
+                                                                        beta, scratch, HW, C, G, rows, eps, act_silu);
   E4T_COUNT_LAUNCH();
   E4T_LAUNCH_CHECK();
-  gn_apply_kernel<1><<<grid, kGNThreads, (size_t)C * sizeof(GNChan) + (size_t)G * sizeof(float2), st>>>(
-      (const bf16*)x, (const bf16*)dy, stats, scratch, gamma, beta, (bf16*)dx, HW, C, G, rows, eps, act_silu);
+  gn_apply_kernel<1><<<grid, threads, 0, st>>>((const bf16*)x, (const bf16*)dy, stats, scratch, gamma, beta, (bf16*)dx,
+                                               HW, C, G, rows, eps, act_silu);
   E4T_COUNT_LAUNCH();
   E4T_LAUNCH_CHECK();
   return 0;
@@ -222,9 +222,7 @@ extern "C" int e4t_groupnorm_bwd(const void* x, const void* dy, const float* gam
 // ---------------------------------------------------------------------------------------------
 // LayerNorm over the last dim (C <= 2048, C % 8 == 0): one warp per row, values held in registers.
 // ---------------------------------------------------------------------------------------------
-static constexpr int kLNMaxIter = 8;
-
-template <int MODE>  // 0 fwd, 1 bwd(dx)
+template <int MODE, int kLNMaxIter>  // MODE 0 fwd, 1 bwd(dx); kLNMaxIter = ceil(C / 256)
 __global__ void __launch_bounds__(256)
 ln_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, const float* __restrict__ gamma,
           const float* __restrict__ beta, bf16* __restrict__ out, float* __restrict__ stats, long rows, int C,
@@ -341,8 +339,11 @@ ln_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, const float* 
 extern "C" int e4t_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* stats,
                                  long long rows, int C, float eps, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
-  E4T_CHECK(C % 8 == 0 && C <= 8 * 32 * kLNMaxIter, "e4t_layernorm_fwd: unsupported C=%d", C);
-  ln_kernel<0><<<cdiv(rows, 8), 256, 0, st>>>((const bf16*)x, nullptr, gamma, beta, (bf16*)y, stats, rows, C, eps);
+  E4T_CHECK(C % 8 == 0 && C <= 2048, "e4t_layernorm_fwd: unsupported C=%d", C);
+  const int it = cdiv(C, 256);
+#define LN_FWD(N) ln_kernel<0, N><<<cdiv(rows, 8), 256, 0, st>>>((const bf16*)x, nullptr, gamma, beta, (bf16*)y, stats, rows, C, eps)
+  if (it <= 2) LN_FWD(2); else if (it <= 3) LN_FWD(3); else if (it <= 5) LN_FWD(5); else LN_FWD(8);
+#undef LN_FWD
   E4T_COUNT_LAUNCH();
   E4T_LAUNCH_CHECK();
   return 0;
@@ -351,9 +352,11 @@ extern "C" int e4t_layernorm_fwd(const void* x, const float* gamma, const float*
 extern "C" int e4t_layernorm_bwd(const void* x, const void* dy, const float* gamma, const float* stats, void* dx,
                                  long long rows, int C, float eps, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
-  E4T_CHECK(C % 8 == 0 && C <= 8 * 32 * kLNMaxIter, "e4t_layernorm_bwd: unsupported C=%d", C);
-  ln_kernel<1><<<cdiv(rows, 8), 256, 0, st>>>((const bf16*)x, (const bf16*)dy, gamma, nullptr, (bf16*)dx,
-                                               const_cast<float*>(stats), rows, C, eps);
+  E4T_CHECK(C % 8 == 0 && C <= 2048, "e4t_layernorm_bwd: unsupported C=%d", C);
+  const int it = cdiv(C, 256);
+#define LN_BWD(N) ln_kernel<1, N><<<cdiv(rows, 8), 256, 0, st>>>((const bf16*)x, (const bf16*)dy, gamma, nullptr, (bf16*)dx, const_cast<float*>(stats), rows, C, eps)
+  if (it <= 2) LN_BWD(2); else if (it <= 3) LN_BWD(3); else if (it <= 5) LN_BWD(5); else LN_BWD(8);
+#undef LN_BWD
   E4T_COUNT_LAUNCH();
   E4T_LAUNCH_CHECK();
   return 0;
