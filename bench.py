@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-micro", action="store_true")
     ap.add_argument("--profile-one-step", action="store_true", help="run W warm-up + 1 step and exit (for ncu)")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the whole-step CUDA graph")
     return ap.parse_args()
 
 
@@ -329,7 +330,8 @@ def main():
         last = None
         for i in range(n):
             hb = batches[i % len(batches)]
-            b = to_device(hb, device) if e2e else hb
+            # e2e: pinned host -> device every step (straight into the graph's static inputs when graphed)
+            b = (hb if step._graph is not None else to_device(hb, device)) if e2e else hb
             out = step(b)
             if e2e:
                 last = out["loss"].item()          # device -> host read of the step result
@@ -349,7 +351,16 @@ def main():
     h2d = batch_bytes(host_batches[0])
 
     # warm-up (also builds the bf16 operand caches and first-call attributes)
-    run_steps(args.warmup, dev_batches, False)
+    run_steps(max(args.warmup, 1), dev_batches, False)
+    cuda_graph = False
+    if not args.no_graph and not args.profile_one_step:
+        try:
+            step.enable_cuda_graph(dev_batches[0], warmup=2)
+            cuda_graph = True
+            run_steps(2, dev_batches, False)
+        except Exception as ex:      # stay on eager launches, say so in the JSON line
+            step._graph = None
+            cuda_graph = f"failed: {type(ex).__name__}: {str(ex)[:200]}"
     if args.profile_one_step:
         run_steps(1, dev_batches, False)
         return
@@ -360,6 +371,13 @@ def main():
     _lib.reset_launch_count()
     t_dev, loss = run_steps(args.steps, dev_batches, False)
     launches = _lib.launch_count()
+    if cuda_graph is True:
+        # under graph replay the host-side counter does not tick: count the launches of one eager step instead
+        step_graph, step._graph = step._graph, None
+        _lib.reset_launch_count()
+        run_steps(1, dev_batches, False)
+        launches = _lib.launch_count() * args.steps
+        step._graph = step_graph
     clocks = sampler.stop() if rank == 0 else None
     value = world * B * args.steps / t_dev
 
@@ -402,7 +420,7 @@ def main():
                 "config": {"workload": "SD-v1.4 E4T pretrain step (UNet enc-half + E4T encoder ViT-H/14 + CLIP text + "
                                        "full UNet + loss + bwd + AdamW), random-init, 512^2 (64x64 latents)",
                            "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
-                           "trainable_params": n_train,
+                           "trainable_params": n_train, "cuda_graph": cuda_graph,
                            "l2": "inputs rotate over 4 batches; per-step working set (activations ~30 GB) >> 126 MB L2",
                            "grad_allreduce": "one NCCL all-reduce of the flat fp32 grad arena" if world > 1 else "none"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches,

@@ -542,9 +542,14 @@ extern "C" int e4t_conv_out_bwd(const float* dy, const float* w, void* dx, int B
 // ---------------------------------------------------------------------------------------------
 // Fused AdamW over a flat fp32 parameter arena (torch.optim.AdamW semantics, amsgrad=False).
 // ---------------------------------------------------------------------------------------------
+__global__ void adamw_tick_kernel(int* step) { *step += 1; }
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                              float* __restrict__ v, long n, float lr, float beta1, float beta2, float eps, float wd,
-                             float bc1, float bc2_sqrt, float grad_scale) {
+                             const int* __restrict__ step_ptr, int step_host, float grad_scale) {
+  // bias corrections from the DEVICE step counter when given (CUDA-graph replays advance it), else the host value
+  const int step = step_ptr ? *step_ptr : step_host;
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
   const long n4 = n / 4;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
     float4 pp = reinterpret_cast<float4*>(p)[i];
@@ -567,7 +572,6 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
     reinterpret_cast<float4*>(m)[i] = mm;
     reinterpret_cast<float4*>(v)[i] = vv;
   }
-  // tail
   for (long i = n4 * 4 + (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     const float gr = g[i] * grad_scale;
     float pv = p[i] * (1.f - lr * wd);
@@ -583,10 +587,22 @@ extern "C" int e4t_adamw_step(float* p, const float* g, float* m, float* v, long
                               float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream_) {
   E4T_CHECK(((uintptr_t)p % 16) == 0 && ((uintptr_t)g % 16) == 0 && ((uintptr_t)m % 16) == 0 && ((uintptr_t)v % 16) == 0,
             "e4t_adamw_step: buffers must be 16-byte aligned");
-  const float bc1 = 1.f - powf(beta1, (float)step);
-  const float bc2 = 1.f - powf(beta2, (float)step);
   adamw_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream_>>>(p, g, m, v, n, lr, beta1, beta2, eps,
-                                                                            weight_decay, bc1, sqrtf(bc2), grad_scale);
+                                                                            weight_decay, nullptr, step, grad_scale);
+  E4T_COUNT_LAUNCH();
+  E4T_LAUNCH_CHECK();
+  return 0;
+}
+// Same, with the step counter in device memory: *step_dev is incremented, then used (CUDA-graph friendly).
+extern "C" int e4t_adamw_step_dev(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
+                                  float beta2, float eps, float weight_decay, int* step_dev, float grad_scale,
+                                  void* stream_) {
+  E4T_CHECK(((uintptr_t)p % 16) == 0 && ((uintptr_t)g % 16) == 0 && ((uintptr_t)m % 16) == 0 && ((uintptr_t)v % 16) == 0,
+            "e4t_adamw_step_dev: buffers must be 16-byte aligned");
+  adamw_tick_kernel<<<1, 1, 0, (cudaStream_t)stream_>>>(step_dev);
+  E4T_COUNT_LAUNCH();
+  adamw_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream_>>>(p, g, m, v, n, lr, beta1, beta2, eps,
+                                                                            weight_decay, step_dev, 0, grad_scale);
   E4T_COUNT_LAUNCH();
   E4T_LAUNCH_CHECK();
   return 0;

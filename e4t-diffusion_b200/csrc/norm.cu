@@ -54,14 +54,13 @@ gn_stats_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, const f
                 const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ sums, int HW,
                 int C, int G, int rows_per_cta, float eps, int act) {
   extern __shared__ __align__(16) uint8_t gsm[];
-  float2* schan = reinterpret_cast<float2*>(gsm);  // [C] per-channel partials
+  float2* schan = reinterpret_cast<float2*>(gsm);  // [rstep][C] per-(row-lane, channel) partials
   const int b = blockIdx.y;
   const int vpr = C / 8;
   const int cv = threadIdx.x % vpr, rl = threadIdx.x / vpr, rstep = blockDim.x / vpr;
   const int c0 = cv * 8;
   const int r0 = blockIdx.x * rows_per_cta;
   const int r1 = min(HW, r0 + rows_per_cta);
-  for (int c = threadIdx.x; c < C; c += blockDim.x) schan[c] = make_float2(0.f, 0.f);
   GNChan ch[8];
   if (MODE == 1) gn_thread_chan(ch, fstats, gamma, beta, b, c0, C, G, 1.f / ((float)HW * (float)(C / G)), eps);
   __syncthreads();
@@ -94,19 +93,17 @@ gn_stats_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, const f
     }
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    atomicAdd(&schan[c0 + j].x, a0[j]);
-    atomicAdd(&schan[c0 + j].y, a1[j]);
-  }
+  for (int j = 0; j < 8; ++j) schan[rl * C + c0 + j] = make_float2(a0[j], a1[j]);
   __syncthreads();
   const int cpg = C / G;
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
     float s = 0.f, ss = 0.f;
-    for (int i = 0; i < cpg; ++i) {
-      const float2 p = schan[g * cpg + i];
-      s += p.x;
-      ss += p.y;
-    }
+    for (int q = 0; q < rstep; ++q)
+      for (int i = 0; i < cpg; ++i) {
+        const float2 p = schan[q * C + g * cpg + i];
+        s += p.x;
+        ss += p.y;
+      }
     atomicAdd(&sums[((long)b * G + g) * 2], s);
     atomicAdd(&sums[((long)b * G + g) * 2 + 1], ss);
   }
@@ -187,7 +184,7 @@ extern "C" int e4t_groupnorm_fwd(const void* x, const float* gamma, const float*
   const int rows = gn_rows_per_cta(B, HW);
   const int threads = gn_block(C);
   dim3 grid(cdiv(HW, rows), B);
-  gn_stats_kernel<0><<<grid, threads, (size_t)C * sizeof(float2), st>>>((const bf16*)x, nullptr, nullptr, nullptr,
+  gn_stats_kernel<0><<<grid, threads, (size_t)(threads / (C / 8)) * C * sizeof(float2), st>>>((const bf16*)x, nullptr, nullptr, nullptr,
                                                                         nullptr, stats, HW, C, G, rows, eps, 0);
   E4T_COUNT_LAUNCH();
   E4T_LAUNCH_CHECK();
@@ -208,7 +205,7 @@ extern "C" int e4t_groupnorm_bwd(const void* x, const void* dy, const float* gam
   const int rows = gn_rows_per_cta(B, HW);
   const int threads = gn_block(C);
   dim3 grid(cdiv(HW, rows), B);
-  gn_stats_kernel<1><<<grid, threads, (size_t)C * sizeof(float2), st>>>((const bf16*)x, (const bf16*)dy, stats, gamma,
+  gn_stats_kernel<1><<<grid, threads, (size_t)(threads / (C / 8)) * C * sizeof(float2), st>>>((const bf16*)x, (const bf16*)dy, stats, gamma,
                                                                         beta, scratch, HW, C, G, rows, eps, act_silu);
   E4T_COUNT_LAUNCH();
   E4T_LAUNCH_CHECK();

@@ -90,6 +90,8 @@ class FlatAdamW:
                     p.grad = self.grad[o:o + p.numel()].view(p.shape)
                     p._e4t_arena = True
         self.step_count = 0
+        self.step_dev = torch.zeros(1, device=dev, dtype=torch.int32)   # device-side counter: graph-replayable
+        FN.DIRECT_GRAD_WRITE = True     # .grad views are zeroed by zero_grad(); WO kernels write them directly
         FN.bump_param_epoch()
         # modules that cache views of re-homed storages refresh themselves lazily (E4TEncoder._stacked)
 
@@ -103,8 +105,8 @@ class FlatAdamW:
 
     def step(self, grad_scale=1.0):
         self.step_count += 1
-        ops.adamw_step(self.arena, self.grad, self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0], self.betas[1],
-                       self.eps, self.weight_decay, self.step_count, grad_scale)
+        ops.adamw_step_dev(self.arena, self.grad, self.exp_avg, self.exp_avg_sq, self.lr, self.betas[0], self.betas[1],
+                           self.eps, self.weight_decay, self.step_dev, grad_scale)
         FN.bump_param_epoch()
 
 
@@ -138,6 +140,7 @@ class PretrainStep:
             self.ehs_e4t = self.text(input_ids=ids)[0].to(weight_dtype)                  # :565-583  (1,77,768)
         self.opt = FlatAdamW(trainable_parameters(unet, e4t_encoder), lr=lr, betas=betas, weight_decay=weight_decay,
                              eps=eps) if optimizer else None
+        self._graph = None
 
     def placeholder_idxs(self, input_ids):
         """[ids.index(placeholder_id) for ids in input_ids] (pretrain_e4t.py:617) — exact integer bookkeeping."""
@@ -168,7 +171,53 @@ class PretrainStep:
         return dict(loss=loss_diff + loss_reg, loss_diff=loss_diff, loss_reg=loss_reg, pred=pred,
                     domain_embed=domain_embed, placeholder_idxs=idxs)
 
+    # ---- whole-step CUDA graph (forward + backward + all-reduce + AdamW) -------------------------------------
+    def enable_cuda_graph(self, example_batch, warmup=3):
+        """Capture one full step into a CUDA graph.  `example_batch` fixes shapes; it must carry `placeholder_idxs`
+        as a device tensor (the host-side index search of pretrain_e4t.py:617 cannot run inside a graph).
+        Afterwards __call__ copies the batch into the static input buffers and replays."""
+        assert self.opt is not None and torch.is_tensor(example_batch.get("placeholder_idxs"))
+        import gc
+        self._static = {k: v.clone() for k, v in example_batch.items()}
+        # Warm-up and capture run on ONE side stream, and every reference to earlier autograd graphs is dropped
+        # first: an AccumulateGrad node that survives from an eager step on the default stream would make the captured
+        # backward synchronise with the legacy stream and invalidate the capture.
+        self._drop_autograd_refs()
+        gc.collect()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                out = self._eager_step(self._static)
+                del out
+            self._drop_autograd_refs()
+        gc.collect()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            out = self._eager_step(self._static)
+            self._static_out = {k: out[k].detach() for k in ("loss", "loss_diff", "loss_reg")}
+            del out
+        self._drop_autograd_refs()
+        self._graph = graph
+        return self
+
+    def _drop_autograd_refs(self):
+        for m in self.unet.modules():
+            c = getattr(m, "_weff_cache", None)
+            if c is not None:
+                c.clear()
+
     def __call__(self, batch):
+        if self._graph is not None:
+            for k, v in batch.items():
+                self._static[k].copy_(v, non_blocking=True)
+            self._graph.replay()
+            return dict(self._static_out)
+        return self._eager_step(batch)
+
+    def _eager_step(self, batch):
         out = self.forward_loss(batch)
         out["loss"].backward()                                                           # :648
         if self.opt is not None:

@@ -246,6 +246,11 @@ class AttentionFn(torch.autograd.Function):
 # ----------------------------------------------------------------------------------------------
 # WeightOffsets: fused effective projection weights of one attention module
 # ----------------------------------------------------------------------------------------------
+# When an arena optimiser owns the gradients (FlatAdamW: every trainable param's .grad is a zeroed view of one flat
+# buffer and each WeightOffsets parameter receives exactly ONE contribution per step), the WO backward kernels write
+# straight into those views instead of returning ~900 small tensors for autograd to add.
+DIRECT_GRAD_WRITE = False
+
 WO_EPOCH = 0  # bumped by every WOEffectiveFn.backward: cached W_eff graphs are single-use
 
 
@@ -279,6 +284,7 @@ class WOEffectiveFn(torch.autograd.Function):
             r0 += W.shape[0]
             saved += [vx, vy, a, b, s]
         ctx.n = n
+        ctx.params = args[n:]     # python refs to the leaf parameters (for direct gradient writes)
         ctx.save_for_backward(*args, *saved)
         carrier = torch.empty((Ctot, R), device=out.device, dtype=F32)
         ctx.mark_non_differentiable(out)
@@ -300,10 +306,17 @@ class WOEffectiveFn(torch.autograd.Function):
             v, w1, b1, w2, b2, Wc, bc, Wr, br = p
             vx, vy, a, b, s = fac[5 * i:5 * i + 5]
             C = W.shape[0]
-            dv, dw1, db1, dw2, db2, dWc, dbc, dWr, dbr = ops.wo_bwd(dW[r0:r0 + C], W, v, w1, w2, Wc, Wr, bc, vx, vy, a,
-                                                                  b, s)
+            plist = ctx.params[9 * i:9 * i + 9]
+            if DIRECT_GRAD_WRITE and all(getattr(q, "_e4t_arena", False) and q.grad is not None for q in plist):
+                outs = [q.grad.view(-1) if q.grad.dim() != 2 else q.grad for q in plist]
+                outs[1] = plist[1].grad.view(-1); outs[3] = plist[3].grad.view(-1)
+                ops.wo_bwd(dW[r0:r0 + C], W, v, w1, w2, Wc, Wr, bc, vx, vy, a, b, s, outs=outs)
+                grads += [None] * 9
+            else:
+                dv, dw1, db1, dw2, db2, dWc, dbc, dWr, dbr = ops.wo_bwd(dW[r0:r0 + C], W, v, w1, w2, Wc, Wr, bc, vx,
+                                                                      vy, a, b, s)
+                grads += [dv, dw1.view_as(w1), db1, dw2.view_as(w2), db2, dWc, dbc, dWr, dbr]
             r0 += C
-            grads += [dv, dw1.view_as(w1), db1, dw2.view_as(w2), db2, dWc, dbc, dWr, dbr]
         return (None,) + (None,) * n + tuple(grads)
 
 

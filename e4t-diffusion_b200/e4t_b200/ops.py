@@ -242,15 +242,21 @@ def wo_weff(W, a, bc, b, s, br, out=None):
     return out
 
 
-def wo_bwd(dWeff, W, v, w1, w2, Wc, Wr, bc, vx, vy, a, b, s):
+def wo_bwd(dWeff, W, v, w1, w2, Wc, Wr, bc, vx, vy, a, b, s, outs=None):
+    """outs: optional 9 preallocated gradient tensors (dv,dw1,db1,dw2,db2,dWc,dbc,dWr,dbr) that are WRITTEN."""
     C, R = W.shape
     dev = W.device
     scratch = torch.empty(3 * C + 2 * R + R + C, device=dev, dtype=F32)
-    dv = torch.empty(1, device=dev, dtype=F32)
-    dw1 = torch.empty(R, device=dev, dtype=F32); db1 = torch.empty(R, device=dev, dtype=F32)
-    dw2 = torch.empty(C, device=dev, dtype=F32); db2 = torch.empty(C, device=dev, dtype=F32)
-    dWc = torch.empty((R, R), device=dev, dtype=F32); dbc = torch.empty(R, device=dev, dtype=F32)
-    dWr = torch.empty((C, C), device=dev, dtype=F32); dbr = torch.empty(C, device=dev, dtype=F32)
+    if outs is not None:
+        dv, dw1, db1, dw2, db2, dWc, dbc, dWr, dbr = outs
+        for t in outs:
+            assert t.dtype == F32 and t.is_contiguous()
+    else:
+        dv = torch.empty(1, device=dev, dtype=F32)
+        dw1 = torch.empty(R, device=dev, dtype=F32); db1 = torch.empty(R, device=dev, dtype=F32)
+        dw2 = torch.empty(C, device=dev, dtype=F32); db2 = torch.empty(C, device=dev, dtype=F32)
+        dWc = torch.empty((R, R), device=dev, dtype=F32); dbc = torch.empty(R, device=dev, dtype=F32)
+        dWr = torch.empty((C, C), device=dev, dtype=F32); dbr = torch.empty(C, device=dev, dtype=F32)
     _lib.call("e4t_wo_bwd", ptr(dWeff), ptr(W), ptr(v), ptr(w1), ptr(w2), ptr(Wc), ptr(Wr), ptr(bc), ptr(vx), ptr(vy),
               ptr(a), ptr(b), ptr(s), ptr(scratch), ptr(dv), ptr(dw1), ptr(db1), ptr(dw2), ptr(db2), ptr(dWc),
               ptr(dbc), ptr(dWr), ptr(dbr), c_int(R), c_int(C), stream())
@@ -261,6 +267,13 @@ def adamw_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale
     assert p.dtype == F32 and p.is_contiguous() and g.is_contiguous() and m.is_contiguous() and v.is_contiguous()
     _lib.call("e4t_adamw_step", ptr(p), ptr(g), ptr(m), ptr(v), c_ll(p.numel()), c_float(lr), c_float(beta1),
               c_float(beta2), c_float(eps), c_float(weight_decay), c_int(step), c_float(grad_scale), stream())
+
+
+def adamw_step_dev(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step_dev, grad_scale=1.0):
+    """AdamW with the step counter in device memory (int32 tensor, incremented by the call): graph-replayable."""
+    assert p.dtype == F32 and step_dev.dtype == torch.int32
+    _lib.call("e4t_adamw_step_dev", ptr(p), ptr(g), ptr(m), ptr(v), c_ll(p.numel()), c_float(lr), c_float(beta1),
+              c_float(beta2), c_float(eps), c_float(weight_decay), ptr(step_dev), c_float(grad_scale), stream())
 
 
 # ----------------------------------------------------------------------------------------------

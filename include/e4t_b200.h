@@ -108,6 +108,9 @@ int e4t_wo_bwd(const float* dWeff, const float* W, const float* v, const float* 
 /* ---- optimiser (torch.optim.AdamW at pretrain_e4t.py:389-392,652) ---------------------------------------------- */
 int e4t_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                    float eps, float weight_decay, int step, float grad_scale, void* stream);
+/* Same with the step counter in device memory (*step_dev is incremented, then used): CUDA-graph replayable. */
+int e4t_adamw_step_dev(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                       float eps, float weight_decay, int* step_dev, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }
