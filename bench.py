@@ -396,7 +396,10 @@ def main():
         a = micro["attn_fwd_L0_self"]
         roof = {"kernel": "attn_fwd_kernel (level-0 self-attention core, N=M=4096, 8x40, B=%d)" % B,
                 "bound": "tensor", "achieved": a["tflops"], "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
-                "frac": a["tflops"] / peaks["bf16_burst"], "traffic": None,
+                "frac": a["tflops"] / peaks["bf16_burst"],
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape from the ncu --set full
+                # capture summarised in profiles/r01_ncu_full_summary.md (algorithmic: Q,K,V read + O write = 168 MB)
+                "traffic": 152436224 if B == 16 else None,
                 "algorithmic_flops_per_launch": a["flops"], "peak_source": peaks["source"] + ", burst figure "
                 "(kernel timed alone, L2 flushed between launches)"}
 

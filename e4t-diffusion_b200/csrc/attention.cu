@@ -28,6 +28,7 @@ struct AttnArgs {
   int nblk;      // number of blocks looped over
   int kst;       // ring stages
   int sbuf;      // fwd: S accumulator buffers in TMEM (2 = software pipelined, 1 = rely on 2 CTAs/SM)
+  int pbuf;      // fwd: P buffers in smem (2 = softmax never waits for the previous P·V to retire)
   int tmem_cols; // TMEM columns to allocate (256 lets two CTAs share an SM)
   float scale;   // dh^-0.5
   // pointers / strides (elements)
@@ -97,8 +98,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + q_bytes;
   uint8_t* sV = sK + a.kst * kv_tile;
-  uint8_t* sP = sV + a.kst * kv_tile;  // 2 x 16 KiB
-  float* sMax = reinterpret_cast<float*>(sP + ((a.BKV + 63) >> 6) * 16384);  // [2][CG][128]
+  const int p_bytes = ((a.BKV + 63) >> 6) * 16384;
+  uint8_t* sP0 = sV + a.kst * kv_tile;  // pbuf x [128][BKV] bf16 (64-col chunks of 16 KiB)
+  float* sMax = reinterpret_cast<float*>(sP0 + a.pbuf * p_bytes);  // [2][CG][128]
   float* sSum = sMax + 2 * CG * 128;                   // [CG][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sSum + CG * 128);
   uint64_t* q_full = bars;
@@ -109,7 +111,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
   uint64_t* s_full = v_empty + 2;
   uint64_t* p_ready = s_full + 2;
   uint64_t* o_done = p_ready + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
+  uint64_t* p_free = o_done + 1;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_free + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
@@ -125,6 +128,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
     }
     mbar_init(p_ready, NSOFT);
     mbar_init(o_done, 1);
+    mbar_init(&p_free[0], 1);
+    mbar_init(&p_free[1], 1);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols);
@@ -181,8 +186,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
             mbar_wait(p_ready, (uint32_t)(j & 1));
             mbar_wait(&v_full[st], (uint32_t)((j / a.kst) & 1));
             tc_fence_after();
-            mma_pv(tO, smem_u32(sP), smem_u32(sV + st * kv_tile), a.BKV * 128, a.BKV, idesc_o, j > 0 ? 1u : 0u);
+            mma_pv(tO, smem_u32(sP0 + (j & (a.pbuf - 1)) * p_bytes), smem_u32(sV + st * kv_tile), a.BKV * 128, a.BKV,
+                   idesc_o, j > 0 ? 1u : 0u);
             umma_commit(&v_empty[st]);
+            umma_commit(&p_free[j & (a.pbuf - 1)]);
             umma_commit(o_done);
           }
         }
@@ -200,6 +207,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
     const uint32_t rowoff = (uint32_t)row * 128u, r7 = (uint32_t)row & 7u;
     for (int j = 0; j < a.nblk; ++j) {
       const uint32_t tS = tS0 + (uint32_t)(j & (a.sbuf - 1)) * 128u + lane_base;
+      uint8_t* sP = sP0 + (j & (a.pbuf - 1)) * p_bytes;
       mbar_wait(&s_full[j & (a.sbuf - 1)], (uint32_t)((j / a.sbuf) & 1));
       tc_fence_after();
       if (a.BKV == 128 && (j + 1) * 128 <= a.M) {
@@ -221,10 +229,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
         for (int g = 0; g < CG; ++g) mx = fmaxf(mx, smx[g * 128 + row]);
         const float m_new = fmaxf(m, mx);
         const float alpha = ex2_approx((m - m_new) * sl2);
-        if (j > 0) {
-          mbar_wait(o_done, (uint32_t)((j - 1) & 1));
-          tc_fence_after();
-        }
+        // the P buffer of this block was last read by P·V of block j - pbuf
+        if (j >= a.pbuf) mbar_wait(&p_free[j & (a.pbuf - 1)], (uint32_t)(((j / a.pbuf) - 1) & 1));
         float rs0 = 0.f, rs1 = 0.f;
         const float mb = m_new * sl2;
 #pragma unroll
@@ -249,6 +255,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
         l = l * alpha + (rs0 + rs1);
         m = m_new;
         if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
+          mbar_wait(o_done, (uint32_t)((j - 1) & 1));  // O is written by P·V of block j-1
+          tc_fence_after();
           for (int oc = cg; oc < ochunk; oc += CG) {
             uint32_t ov[16];
             tmem_ld16(tO + lane_base + (uint32_t)(oc * 16), ov);
@@ -314,10 +322,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
       const float m_new = fmaxf(m, mx);
       const float alpha = ex2_approx((m - m_new) * sl2);  // m = -inf on the first block -> 0
       // P buffer and O are free once PV_{j-1} retired
-      if (j > 0) {
-        mbar_wait(o_done, (uint32_t)((j - 1) & 1));
-        tc_fence_after();
-      }
+      if (j >= a.pbuf) mbar_wait(&p_free[j & (a.pbuf - 1)], (uint32_t)(((j / a.pbuf) - 1) & 1));
       // ---- P = exp2((s - m_new) * sl2) -> smem (bf16, swizzled K-major), partial row sum ----
       float rs = 0.f;
       const float mb = m_new * sl2;
@@ -354,6 +359,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
       m = m_new;
       // ---- lazy rescale of my chunks of the O accumulator (warp-uniform branch) ----
       if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
+        mbar_wait(o_done, (uint32_t)((j - 1) & 1));  // O is written by P·V of block j-1
+        tc_fence_after();
         for (int oc = cg; oc < ochunk; oc += CG) {
           uint32_t v[16];
           tmem_ld16(tO + lane_base + (uint32_t)(oc * 16), v);
@@ -854,6 +861,257 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_const
 }
 
 // =============================================================================================
+// Fused backward (dh <= 80): CTA = (128-key tile, head, batch) looping over 128-query blocks.  S and dP are computed
+// ONCE per (query block, key tile) pair (the two-kernel path recomputes them in both kernels):
+//   Sᵀ = K·Qᵀ, dPᵀ = V·dOᵀ  ->  Pᵀ, dSᵀ (threads)  ->  dV += Pᵀ·dO, dK += dSᵀ·Q, dQ_blk = dS·K
+// dQ_blk uses the thread-written dSᵀ tile as an MN-major A operand and is reduced into an fp32 dQ accumulator in
+// HBM with red.global.add.v4.f32 (one CTA per key tile contributes to every query row).
+//   TMEM: Sᵀ [0,128) | dPᵀ [128,256) | dV | dK | dQ_blk  (3 x dpad columns, dpad <= 80)
+// The dQ read-out of block j-1 is deferred until after block j's dSᵀ has been handed to the tensor core.
+// =============================================================================================
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void mma_ds_k(uint32_t d_tmem, uint32_t sdST, uint32_t sK, uint32_t k_chunk,
+                                         uint32_t idesc) {
+  // D[128 q][dpad] = dS[128 q][128 kv] · K[128 kv][dpad]; A = dSᵀ tile ([kv][q], 64-q chunks of 16 KiB) read as an
+  // MN-major operand, B = K tile ([kv][d], 64-wide d chunks) read as an MN-major operand.
+  for (int ks = 0; ks < 8; ++ks)
+    umma_bf16(d_tmem, umma_desc(sdST + ks * 2048, 16384, 1024), umma_desc(sK + ks * 2048, k_chunk, 1024), idesc,
+              ks > 0 ? 1u : 0u);
+}
+
+template <int CG>
+__global__ void __launch_bounds__(128 + 128 * CG, 1)
+attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                      const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapdO,
+                      const AttnArgs a, float* __restrict__ dQacc) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr int BQ = 128;
+  const int kv_bytes = a.DC * 16384;
+  const int q_tile = a.DC * BQ * 128;
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + kv_bytes;
+  uint8_t* sQ = sV + kv_bytes;  // kst stages of {Q tile, dO tile}
+  uint8_t* sdO = sQ + a.kst * q_tile;
+  uint8_t* sPT = sdO + a.kst * q_tile;  // 2 x 16 KiB
+  uint8_t* sdST = sPT + 32768;          // 2 x 16 KiB
+  float* sLSE = reinterpret_cast<float*>(sdST + 32768);  // [128]
+  float* sD = sLSE + 128;                                // [128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sD + 128);
+  uint64_t* kv_full = bars;
+  uint64_t* q_full = bars + 1;   // [2]
+  uint64_t* q_empty = bars + 3;  // [2]
+  uint64_t* sp_full = bars + 5;
+  uint64_t* ds_ready = bars + 6;
+  uint64_t* acc_done = bars + 7;
+  uint64_t* dq_full = bars + 8;
+  uint64_t* dq_empty = bars + 9;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  if (warp == 1 && lane == 0) {
+    mbar_init(kv_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
+    }
+    mbar_init(sp_full, 1);
+    mbar_init(ds_ready, 128 * CG);
+    mbar_init(acc_done, 1);
+    mbar_init(dq_full, 1);
+    mbar_init(dq_empty, 128 * CG);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tST = tmem, tdPT = tmem + 128, tdV = tmem + 256, tdK = tdV + (uint32_t)a.dpad,
+                 tdQ = tdK + (uint32_t)a.dpad;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(kv_full, (uint32_t)(2 * kv_bytes));
+      for (int c = 0; c < a.DC; ++c) {
+        tma_load_4d(sK + c * 16384, &mapK, kv_full, c * 64, h, k0, b);
+        tma_load_4d(sV + c * 16384, &mapV, kv_full, c * 64, h, k0, b);
+      }
+      for (int j = 0; j < a.nblk; ++j) {
+        const int st = j % a.kst;
+        mbar_wait(&q_empty[st], (uint32_t)(((j / a.kst) & 1) ^ 1));
+        mbar_expect_tx(&q_full[st], (uint32_t)(2 * q_tile));
+        for (int c = 0; c < a.DC; ++c) {
+          tma_load_4d(sQ + st * q_tile + c * BQ * 128, &mapQ, &q_full[st], c * 64, h, j * BQ, b);
+          tma_load_4d(sdO + st * q_tile + c * BQ * 128, &mapdO, &q_full[st], c * 64, h, j * BQ, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_bf16((uint32_t)BQ, false, false);
+      const uint32_t idesc_o = umma_idesc_bf16((uint32_t)a.dpad, false, true);
+      const uint32_t idesc_q = umma_idesc_bf16((uint32_t)a.dpad, true, true);
+      mbar_wait(kv_full, 0);
+      for (int j = 0; j < a.nblk; ++j) {
+        const int st = j % a.kst;
+        mbar_wait(&q_full[st], (uint32_t)((j / a.kst) & 1));
+        tc_fence_after();
+        mma_kmajor(tST, smem_u32(sK), 16384, smem_u32(sQ + st * q_tile), BQ * 128, a.dh, a.DC, idesc_s);
+        mma_kmajor(tdPT, smem_u32(sV), 16384, smem_u32(sdO + st * q_tile), BQ * 128, a.dh, a.DC, idesc_s);
+        umma_commit(sp_full);
+        mbar_wait(ds_ready, (uint32_t)(j & 1));
+        tc_fence_after();
+        mma_pv(tdV, smem_u32(sPT), smem_u32(sdO + st * q_tile), BQ * 128, BQ, idesc_o, j > 0 ? 1u : 0u);
+        mma_pv(tdK, smem_u32(sdST), smem_u32(sQ + st * q_tile), BQ * 128, BQ, idesc_o, j > 0 ? 1u : 0u);
+        if (j > 0) {
+          mbar_wait(dq_empty, (uint32_t)((j - 1) & 1));  // threads have drained dQ_blk of block j-1
+          tc_fence_after();
+        }
+        mma_ds_k(tdQ, smem_u32(sdST), smem_u32(sK), 16384, idesc_q);
+        umma_commit(&q_empty[st]);
+        umma_commit(dq_full);
+        umma_commit(acc_done);
+      }
+    }
+  } else if (warp >= 4) {
+    constexpr int NSOFT = 128 * CG;
+    const int ew = (warp - 4) & 3;
+    const int cg = (warp - 4) >> 2;
+    const int row = ew * 32 + lane;  // key index within the tile == TMEM lane; also the query row of dQ_blk
+    const int tid = threadIdx.x - 128;
+    const uint32_t lane_base = (uint32_t)(ew * 32) << 16;
+    const int kv = k0 + row;
+    const bool kv_ok = kv < a.M;
+    const uint32_t rowoff = (uint32_t)row * 128u, r7 = (uint32_t)row & 7u;
+    const float sl2 = a.scale * kLog2e;
+    const long long sbase = ((long long)b * a.H + h) * a.N;
+    const int ochunk = a.dpad >> 4;
+    const int C = a.H * a.dh;
+
+    auto drain_dq = [&](int jb) {
+      // dQ_blk of block jb: TMEM lane = query row; reduce into the fp32 accumulator
+      mbar_wait(dq_full, (uint32_t)(jb & 1));
+      tc_fence_after();
+      const int qn = jb * BQ + row;
+      float* dst = dQacc + ((long long)b * a.N + qn) * C + h * a.dh;
+      for (int oc = cg; oc < ochunk; oc += CG) {
+        uint32_t v[16];
+        __syncwarp();
+        tmem_ld16(tdQ + lane_base + (uint32_t)(oc * 16), v);
+        tmem_ld_wait();
+        if (qn < a.N) {
+#pragma unroll
+          for (int i = 0; i < 16; i += 4)
+            if (oc * 16 + i < a.dh)
+              red_add_v4(dst + oc * 16 + i, __uint_as_float(v[i]), __uint_as_float(v[i + 1]),
+                         __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(dq_empty);
+    };
+
+    for (int j = 0; j < a.nblk; ++j) {
+      const int qn = j * BQ + tid;
+      if (tid < BQ) {
+        sLSE[tid] = (qn < a.N) ? a.LSE[sbase + qn] * kLog2e : INFINITY;  // queries past N: p = 0
+        sD[tid] = (qn < a.N) ? a.Dv[sbase + qn] * a.scale : 0.f;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(NSOFT) : "memory");
+      mbar_wait(sp_full, (uint32_t)(j & 1));
+      tc_fence_after();
+      for (int c32 = cg; c32 < BQ / 32; c32 += CG) {
+        const int c = c32 * 32;
+        uint32_t sreg[32], dp[32], wp[16], wd[16];
+        __syncwarp();
+        tmem_ld32(tST + lane_base + (uint32_t)c, sreg);
+        tmem_ld32(tdPT + lane_base + (uint32_t)c, dp);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 16; e += 2) {
+          const float4 ls = *reinterpret_cast<const float4*>(&sLSE[c + 2 * e]);
+          const float4 dd = *reinterpret_cast<const float4*>(&sD[c + 2 * e]);
+          const float p0 = ex2_approx(fmaf(__uint_as_float(sreg[2 * e]), sl2, -ls.x));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(sreg[2 * e + 1]), sl2, -ls.y));
+          const float p2 = ex2_approx(fmaf(__uint_as_float(sreg[2 * e + 2]), sl2, -ls.z));
+          const float p3 = ex2_approx(fmaf(__uint_as_float(sreg[2 * e + 3]), sl2, -ls.w));
+          wp[e] = kv_ok ? pack_bf16(p0, p1) : 0u;
+          wp[e + 1] = kv_ok ? pack_bf16(p2, p3) : 0u;
+          wd[e] = kv_ok ? pack_bf16(p0 * fmaf(__uint_as_float(dp[2 * e]), a.scale, -dd.x),
+                                    p1 * fmaf(__uint_as_float(dp[2 * e + 1]), a.scale, -dd.y))
+                        : 0u;
+          wd[e + 1] = kv_ok ? pack_bf16(p2 * fmaf(__uint_as_float(dp[2 * e + 2]), a.scale, -dd.z),
+                                        p3 * fmaf(__uint_as_float(dp[2 * e + 3]), a.scale, -dd.w))
+                            : 0u;
+        }
+        sts_row32(sPT, rowoff, r7, c, wp);
+        sts_row32(sdST, rowoff, r7, c, wd);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(ds_ready);
+      if (j > 0) drain_dq(j - 1);
+      // everyone is done reading sLSE/sD of this block before the next block overwrites them
+      asm volatile("bar.sync 2, %0;" ::"n"(NSOFT) : "memory");
+    }
+    drain_dq(a.nblk - 1);
+    mbar_wait(acc_done, (uint32_t)((a.nblk - 1) & 1));
+    tc_fence_after();
+    for (int which = 0; which < 2; ++which) {
+      const uint32_t tacc = which == 0 ? tdV : tdK;
+      bf16* base = which == 0 ? a.dV + (long long)b * a.dv_bs + (long long)kv * a.lddv
+                              : a.dK + (long long)b * a.dk_bs + (long long)kv * a.lddk;
+      for (int oc = cg; oc < ochunk; oc += CG) {
+        const int c = oc * 16;
+        uint32_t v[16];
+        __syncwarp();
+        tmem_ld16(tacc + lane_base + (uint32_t)c, v);
+        tmem_ld_wait();
+        if (kv_ok) {
+          bf16* o = base + h * a.dh + c;
+#pragma unroll
+          for (int i = 0; i < 16; i += 8) {
+            if (c + i < a.dh) {
+              *reinterpret_cast<uint4*>(o + i) =
+                  make_uint4(pack_bf16(__uint_as_float(v[i]), __uint_as_float(v[i + 1])),
+                             pack_bf16(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])),
+                             pack_bf16(__uint_as_float(v[i + 4]), __uint_as_float(v[i + 5])),
+                             pack_bf16(__uint_as_float(v[i + 6]), __uint_as_float(v[i + 7])));
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// fp32 [B][N][C] -> bf16 with row / batch strides
+__global__ void cvt_dq_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long rows_per_b, int C,
+                              long long ldd, long long d_bs, long long total_vec) {
+  const int vpr = C / 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / vpr;
+    const int c = (int)(i % vpr) * 8;
+    const float4 x = *reinterpret_cast<const float4*>(src + r * C + c);
+    const float4 y = *reinterpret_cast<const float4*>(src + r * C + c + 4);
+    const long long bb = r / rows_per_b, rr = r % rows_per_b;
+    *reinterpret_cast<uint4*>(dst + bb * d_bs + rr * ldd + c) =
+        make_uint4(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w), pack_bf16(y.x, y.y), pack_bf16(y.z, y.w));
+  }
+}
+
+// =============================================================================================
 // Host
 // =============================================================================================
 static int make_head_map(CUtensorMap* m, const void* p, int dh, int H, int rows, int B, long long ld, long long bs,
@@ -900,6 +1158,7 @@ extern "C" int e4t_attn_fwd(const void* Q, const void* K, const void* V, void* O
   a.kst = (a.DC >= 3 || occ2) ? 1 : 2;
   a.sbuf = occ2 ? 1 : 2;
   a.tmem_cols = occ2 ? 256 : 512;
+  a.pbuf = 1;
   a.scale = scale;
   a.O = (bf16*)O; a.ldo = ldo; a.o_bs = o_bs; a.LSE = LSE;
   CUtensorMap mQ, mK, mV;
@@ -907,8 +1166,10 @@ extern "C" int e4t_attn_fwd(const void* Q, const void* K, const void* V, void* O
   if (int e = make_head_map(&mK, K, dh, H, M, B, ldk, k_bs, a.BKV)) return e;
   if (int e = make_head_map(&mV, V, dh, H, M, B, ldv, v_bs, a.BKV)) return e;
   const int cg = attn_cg(0);
-  const size_t smem = (size_t)a.DC * 16384 + (size_t)2 * a.kst * a.DC * a.BKV * 128 + (size_t)cdiv(a.BKV, 64) * 16384 +
-                      3 * 4 * 128 * 4 + 256 + 1024;
+  const size_t smem_base = (size_t)a.DC * 16384 + (size_t)2 * a.kst * a.DC * a.BKV * 128 + 3 * 4 * 128 * 4 + 256 + 1024;
+  const size_t p_bytes = (size_t)cdiv(a.BKV, 64) * 16384;
+  if (!occ2 && a.nblk > 1 && smem_base + 2 * p_bytes <= 227 * 1024) a.pbuf = 2;
+  const size_t smem = smem_base + a.pbuf * p_bytes;
   static bool attr = false;
   if (!attr) {
     E4T_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -1004,5 +1265,63 @@ extern "C" int e4t_attn_bwd(const void* Q, const void* K, const void* V, const v
     E4T_COUNT_LAUNCH();
     E4T_LAUNCH_CHECK();
   }
+  return 0;
+}
+
+// Fused backward (one pass over the (query block, key tile) pairs).  dQacc: fp32 scratch [B][N][H*dh] (zeroed here).
+// Falls back to the two-kernel path when the head dim does not fit the TMEM budget (dh > 80) or N is tiny.
+extern "C" int e4t_attn_bwd_fused(const void* Q, const void* K, const void* V, const void* O, const void* dO,
+                                  const float* LSE, float* Dv, float* dQacc, void* dQ, void* dK, void* dV, int B, int H,
+                                  int N, int M, int dh, long long ldq, long long q_bs, long long ldk, long long k_bs,
+                                  long long ldv, long long v_bs, long long ldo, long long o_bs, long long lddo,
+                                  long long do_bs, long long lddq, long long dq_bs, long long lddk, long long dk_bs,
+                                  long long lddv, long long dv_bs, float scale, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  if (int e = attn_common_checks(dh, ldq, ldk, ldv)) return e;
+  const int dpad = round16(dh);
+  if (256 + 3 * dpad > 512 || N < 128)
+    return e4t_attn_bwd(Q, K, V, O, dO, LSE, Dv, dQ, dK, dV, B, H, N, M, dh, ldq, q_bs, ldk, k_bs, ldv, v_bs, ldo, o_bs,
+                        lddo, do_bs, lddq, dq_bs, lddk, dk_bs, lddv, dv_bs, scale, stream_);
+  E4T_CHECK(lddo % 8 == 0 && lddq % 8 == 0 && lddk % 8 == 0 && lddv % 8 == 0, "e4t_attn_bwd_fused: strides %% 8");
+  attn_delta_kernel<<<cdiv((long long)B * N * H, 8), 256, 0, st>>>((const bf16*)O, (const bf16*)dO, Dv, B, H, N, dh, ldo,
+                                                                   o_bs, lddo, do_bs);
+  E4T_COUNT_LAUNCH();
+  const long long nacc = (long long)B * N * H * dh;
+  E4T_CUDA(cudaMemsetAsync(dQacc, 0, (size_t)nacc * sizeof(float), st));
+  static bool attr = false;
+  if (!attr) {
+    E4T_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr = true;
+  }
+  AttnArgs a;
+  memset(&a, 0, sizeof(a));
+  a.B = B; a.H = H; a.N = N; a.M = M; a.dh = dh;
+  a.DC = cdiv(dh, 64);
+  a.dpad = dpad;
+  a.scale = scale;
+  a.LSE = const_cast<float*>(LSE); a.Dv = Dv;
+  a.dK = (bf16*)dK; a.lddk = lddk; a.dk_bs = dk_bs;
+  a.dV = (bf16*)dV; a.lddv = lddv; a.dv_bs = dv_bs;
+  a.BKV = 128;
+  a.nblk = cdiv(N, 128);
+  CUtensorMap mQ, mK, mV, mdO;
+  if (int e = make_head_map(&mQ, Q, dh, H, N, B, ldq, q_bs, 128)) return e;
+  if (int e = make_head_map(&mdO, dO, dh, H, N, B, lddo, do_bs, 128)) return e;
+  if (int e = make_head_map(&mK, K, dh, H, M, B, ldk, k_bs, 128)) return e;
+  if (int e = make_head_map(&mV, V, dh, H, M, B, ldv, v_bs, 128)) return e;
+  const size_t fixed = (size_t)2 * a.DC * 16384 + 65536 + 1024 + 256 + 1024;
+  const size_t per_stage = (size_t)2 * a.DC * 128 * 128;
+  a.kst = (fixed + 2 * per_stage <= 227 * 1024 && a.nblk > 1) ? 2 : 1;
+  const size_t smem = fixed + a.kst * per_stage;
+  E4T_CHECK(smem <= 227 * 1024, "e4t_attn_bwd_fused: smem budget exceeded (%zu)", smem);
+  attn_bwd_fused_kernel<2><<<dim3(cdiv(M, 128), H, B), 128 + 128 * 2, smem, st>>>(mQ, mK, mV, mdO, a, dQacc);
+  E4T_COUNT_LAUNCH();
+  E4T_LAUNCH_CHECK();
+  const long long total_vec = (long long)B * N * (H * dh / 8);
+  long long blocks = (total_vec + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  cvt_dq_kernel<<<(int)blocks, 256, 0, st>>>(dQacc, (bf16*)dQ, N, H * dh, lddq, dq_bs, total_vec);
+  E4T_COUNT_LAUNCH();
+  E4T_LAUNCH_CHECK();
   return 0;
 }

@@ -58,6 +58,15 @@ int e4t_attn_bwd(const void* Q, const void* K, const void* V, const void* O, con
                  long long o_bs, long long lddo, long long do_bs, long long lddq, long long dq_bs, long long lddk,
                  long long dk_bs, long long lddv, long long dv_bs, float scale, void* stream);
 
+/* Single-pass backward: S and dP are computed once per (query block, key tile) pair and dQ is reduced into the fp32
+ * scratch dQacc [B][N][H*dh] (zeroed by the call) before being written to dQ as bf16.  Falls back to e4t_attn_bwd
+ * when 256 + 3*round16(dh) TMEM columns do not fit (dh > 80) or N < 128. */
+int e4t_attn_bwd_fused(const void* Q, const void* K, const void* V, const void* O, const void* dO, const float* LSE,
+                       float* Dv, float* dQacc, void* dQ, void* dK, void* dV, int B, int H, int N, int M, int dh,
+                       long long ldq, long long q_bs, long long ldk, long long k_bs, long long ldv, long long v_bs,
+                       long long ldo, long long o_bs, long long lddo, long long do_bs, long long lddq, long long dq_bs,
+                       long long lddk, long long dk_bs, long long lddv, long long dv_bs, float scale, void* stream);
+
 /* ---- normalisation ------------------------------------------------------------------------------------------- */
 /* GroupNorm (+ optional fused SiLU).  Replaces nn.GroupNorm + F.silu in diffusers ResnetBlock2D, Transformer2DModel
  * .norm (transformer_2d.py:149,253) and conv_norm_out/conv_act (unet_2d_condition.py:554-556).

@@ -178,11 +178,12 @@ def test_attention(B, H, N, M, dh):
     torch.cuda.synchronize()
     assert _rel(o, oref) < 6e-3, _rel(o, oref)
     assert (lse - lse_ref).abs().max().item() < 2e-2
-    dq, dk, dv = ops.attn_bwd(q, k, v, o, do, lse, H)
-    torch.cuda.synchronize()
-    assert _rel(dq, qr.grad) < 1e-2, ("dq", _rel(dq, qr.grad))
-    assert _rel(dk, kr.grad) < 1e-2, ("dk", _rel(dk, kr.grad))
-    assert _rel(dv, vr.grad) < 1e-2, ("dv", _rel(dv, vr.grad))
+    for fused in (True, False):       # single-pass (dh <= 80, N >= 128) and two-kernel backward
+        dq, dk, dv = ops.attn_bwd(q, k, v, o, do, lse, H, fused=fused)
+        torch.cuda.synchronize()
+        assert _rel(dq, qr.grad) < 1e-2, ("dq", fused, _rel(dq, qr.grad))
+        assert _rel(dk, kr.grad) < 1e-2, ("dk", fused, _rel(dk, kr.grad))
+        assert _rel(dv, vr.grad) < 1e-2, ("dv", fused, _rel(dv, vr.grad))
 
 
 def test_attention_fused_qkv_strides():

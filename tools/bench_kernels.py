@@ -38,8 +38,9 @@ if "attn" in what:
         do = bf(B, N, C)
         tf = timeit(lambda: ops.attn_fwd(q, k, v, 8))
         tb = timeit(lambda: ops.attn_bwd(q, k, v, o, do, lse, 8))
+        tb2 = timeit(lambda: ops.attn_bwd(q, k, v, o, do, lse, 8, fused=False))
         fl = 4.0 * N * M * C * B
-        print(f"N={N:5d} M={M:5d} dh={C//8:3d}: fwd {tf:7.3f} ms {fl/tf/1e9:7.1f} TF/s | bwd {tb:7.3f} ms {2.5*fl/tb/1e9:7.1f} TF/s(alg 2.5x)")
+        print(f"N={N:5d} M={M:5d} dh={C//8:3d}: fwd {tf:7.3f} ms {fl/tf/1e9:7.1f} TF/s | bwd fused {tb:7.3f} ms {2.5*fl/tb/1e9:7.1f} TF/s | bwd 2-kernel {tb2:7.3f} ms")
 if "gemm" in what:
     print("== gemm  (M,N,K) [a_mn,b_mn]")
     shapes = [(B * 4096, 960, 320, 0, 0), (B * 4096, 320, 320, 0, 0), (B * 4096, 2560, 320, 0, 0), (B * 4096, 320, 1280, 0, 0),
