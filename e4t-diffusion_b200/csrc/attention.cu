@@ -1024,32 +1024,40 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
       asm volatile("bar.sync 1, %0;" ::"n"(NSOFT) : "memory");
       mbar_wait(sp_full, (uint32_t)(j & 1));
       tc_fence_after();
-      for (int c32 = cg; c32 < BQ / 32; c32 += CG) {
-        const int c = c32 * 32;
-        uint32_t sreg[32], dp[32], wp[16], wd[16];
+      // 16-column chunks (two TMEM loads in flight per chunk); chunk c16 belongs to column group (c16 % CG)
+      for (int c16 = cg; c16 < BQ / 16; c16 += CG) {
+        const int c = c16 * 16;
+        uint32_t sreg[16], dp[16], wp[8], wd[8];
         __syncwarp();
-        tmem_ld32(tST + lane_base + (uint32_t)c, sreg);
-        tmem_ld32(tdPT + lane_base + (uint32_t)c, dp);
+        tmem_ld16(tST + lane_base + (uint32_t)c, sreg);
+        tmem_ld16(tdPT + lane_base + (uint32_t)c, dp);
         tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 16; e += 2) {
+        for (int e = 0; e < 8; e += 2) {
           const float4 ls = *reinterpret_cast<const float4*>(&sLSE[c + 2 * e]);
           const float4 dd = *reinterpret_cast<const float4*>(&sD[c + 2 * e]);
           const float p0 = ex2_approx(fmaf(__uint_as_float(sreg[2 * e]), sl2, -ls.x));
           const float p1 = ex2_approx(fmaf(__uint_as_float(sreg[2 * e + 1]), sl2, -ls.y));
           const float p2 = ex2_approx(fmaf(__uint_as_float(sreg[2 * e + 2]), sl2, -ls.z));
           const float p3 = ex2_approx(fmaf(__uint_as_float(sreg[2 * e + 3]), sl2, -ls.w));
-          wp[e] = kv_ok ? pack_bf16(p0, p1) : 0u;
-          wp[e + 1] = kv_ok ? pack_bf16(p2, p3) : 0u;
-          wd[e] = kv_ok ? pack_bf16(p0 * fmaf(__uint_as_float(dp[2 * e]), a.scale, -dd.x),
-                                    p1 * fmaf(__uint_as_float(dp[2 * e + 1]), a.scale, -dd.y))
-                        : 0u;
-          wd[e + 1] = kv_ok ? pack_bf16(p2 * fmaf(__uint_as_float(dp[2 * e + 2]), a.scale, -dd.z),
-                                        p3 * fmaf(__uint_as_float(dp[2 * e + 3]), a.scale, -dd.w))
-                            : 0u;
+          wp[e] = pack_bf16(p0, p1);
+          wp[e + 1] = pack_bf16(p2, p3);
+          wd[e] = pack_bf16(p0 * fmaf(__uint_as_float(dp[2 * e]), a.scale, -dd.x),
+                            p1 * fmaf(__uint_as_float(dp[2 * e + 1]), a.scale, -dd.y));
+          wd[e + 1] = pack_bf16(p2 * fmaf(__uint_as_float(dp[2 * e + 2]), a.scale, -dd.z),
+                                p3 * fmaf(__uint_as_float(dp[2 * e + 3]), a.scale, -dd.w));
         }
-        sts_row32(sPT, rowoff, r7, c, wp);
-        sts_row32(sdST, rowoff, r7, c, wd);
+        if (!kv_ok) {   // keys past M (only in the last key tile): contribute nothing
+#pragma unroll
+          for (int e = 0; e < 8; ++e) wp[e] = wd[e] = 0u;
+        }
+        uint8_t* pp = sPT + (c >> 6) * 16384 + rowoff;
+        uint8_t* pd = sdST + (c >> 6) * 16384 + rowoff;
+        const uint32_t cb = (uint32_t)((c & 63) >> 3);
+        *reinterpret_cast<uint4*>(pp + ((cb ^ r7) << 4)) = make_uint4(wp[0], wp[1], wp[2], wp[3]);
+        *reinterpret_cast<uint4*>(pp + (((cb + 1) ^ r7) << 4)) = make_uint4(wp[4], wp[5], wp[6], wp[7]);
+        *reinterpret_cast<uint4*>(pd + ((cb ^ r7) << 4)) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+        *reinterpret_cast<uint4*>(pd + (((cb + 1) ^ r7) << 4)) = make_uint4(wd[4], wd[5], wd[6], wd[7]);
       }
       fence_proxy_async_smem();
       tc_fence_before();
@@ -1291,6 +1299,7 @@ extern "C" int e4t_attn_bwd_fused(const void* Q, const void* K, const void* V, c
   static bool attr = false;
   if (!attr) {
     E4T_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    E4T_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr = true;
   }
   AttnArgs a;
@@ -1314,7 +1323,8 @@ extern "C" int e4t_attn_bwd_fused(const void* Q, const void* K, const void* V, c
   a.kst = (fixed + 2 * per_stage <= 227 * 1024 && a.nblk > 1) ? 2 : 1;
   const size_t smem = fixed + a.kst * per_stage;
   E4T_CHECK(smem <= 227 * 1024, "e4t_attn_bwd_fused: smem budget exceeded (%zu)", smem);
-  attn_bwd_fused_kernel<2><<<dim3(cdiv(M, 128), H, B), 128 + 128 * 2, smem, st>>>(mQ, mK, mV, mdO, a, dQacc);
+  if (attn_cg(1) == 4) attn_bwd_fused_kernel<4><<<dim3(cdiv(M, 128), H, B), 128 + 128 * 4, smem, st>>>(mQ, mK, mV, mdO, a, dQacc);
+  else attn_bwd_fused_kernel<2><<<dim3(cdiv(M, 128), H, B), 128 + 128 * 2, smem, st>>>(mQ, mK, mV, mdO, a, dQacc);
   E4T_COUNT_LAUNCH();
   E4T_LAUNCH_CHECK();
   const long long total_vec = (long long)B * N * (H * dh / 8);
