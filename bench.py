@@ -305,7 +305,8 @@ def main():
     device = torch.device("cuda", local)
     import torch.distributed as dist
     if world > 1:
-        dist.init_process_group("nccl", device_id=device)
+        import datetime
+        dist.init_process_group("nccl", device_id=device, timeout=datetime.timedelta(seconds=180))
     from e4t_b200 import _lib
     from e4t_b200.engine import PretrainStep
     _lib.load()

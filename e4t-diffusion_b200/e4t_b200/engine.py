@@ -186,6 +186,11 @@ class PretrainStep:
         gc.collect()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
+        # Data parallel runs keep the NCCL all-reduce and the optimiser kernel OUTSIDE the graph (three eager launches):
+        # collectives captured into a graph must be captured identically on every rank and interact with the
+        # process-group watchdog; the compute part (forward + backward) is what has thousands of launches.
+        self._graph_has_opt = not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
+        body = self._eager_step if self._graph_has_opt else self._fwd_bwd
         with torch.cuda.stream(side):
             for _ in range(warmup):
                 out = self._eager_step(self._static)
@@ -196,7 +201,7 @@ class PretrainStep:
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph, stream=side):
-            out = self._eager_step(self._static)
+            out = body(self._static)
             self._static_out = {k: out[k].detach() for k in ("loss", "loss_diff", "loss_reg")}
             del out
         self._drop_autograd_refs()
@@ -214,14 +219,23 @@ class PretrainStep:
             for k, v in batch.items():
                 self._static[k].copy_(v, non_blocking=True)
             self._graph.replay()
+            if not self._graph_has_opt:
+                self._apply_optimizer()
             return dict(self._static_out)
         return self._eager_step(batch)
 
-    def _eager_step(self, batch):
+    def _fwd_bwd(self, batch):
         out = self.forward_loss(batch)
         out["loss"].backward()                                                           # :648
+        return out
+
+    def _apply_optimizer(self):
         if self.opt is not None:
             scale = self.opt.all_reduce_grads()
             self.opt.step(scale)                                                         # :652
             self.opt.zero_grad()                                                         # :654
+
+    def _eager_step(self, batch):
+        out = self._fwd_bwd(batch)
+        self._apply_optimizer()
         return out
