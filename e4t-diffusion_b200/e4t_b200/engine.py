@@ -200,7 +200,8 @@ class PretrainStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, stream=side):
+        mode = "global" if self._graph_has_opt else "thread_local"   # NCCL's watchdog thread polls events
+        with torch.cuda.graph(graph, stream=side, capture_error_mode=mode):
             out = body(self._static)
             self._static_out = {k: out[k].detach() for k in ("loss", "loss_diff", "loss_reg")}
             del out
