@@ -607,3 +607,219 @@ extern "C" int e4t_adamw_step_dev(float* p, const float* g, float* m, float* v, 
   E4T_LAUNCH_CHECK();
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// WeightOffsets BANK: the same kernels as above, batched over ALL projections of a UNet (96 for SD-v1.4) so that
+// a step needs 2 forward + 5 backward launches instead of ~1000 tiny ones.  `tab` is a device array of WOProj
+// (one per projection), built once by the host binding from the module tree.
+// ---------------------------------------------------------------------------------------------
+struct WOProj {
+  const float *W, *v, *w1, *b1, *w2, *b2, *Wc, *bc, *Wr, *br;  // parameters (fp32)
+  float* fac;      // forward scratch : vx[R] a[R] vy[C] b[C] s[C]
+  float* bw;       // backward scratch: Ga[C] Gbc[C] G1[C] GTb[R] GTs[R] dvx[R] dvy[C]   (zeroed per backward)
+  bf16* weff;      // [C][R] slice of the fused W_eff storage
+  const float* dweff;  // [C][R] slice of the accumulated weight gradient
+  float *dv, *dw1, *db1, *dw2, *db2, *dWc, *dbc, *dWr, *dbr;  // gradient destinations (written)
+  int R, C;
+};
+__device__ __forceinline__ float* wo_vx(const WOProj& p) { return p.fac; }
+__device__ __forceinline__ float* wo_a(const WOProj& p) { return p.fac + p.R; }
+__device__ __forceinline__ float* wo_vy(const WOProj& p) { return p.fac + 2 * p.R; }
+__device__ __forceinline__ float* wo_b(const WOProj& p) { return p.fac + 2 * p.R + p.C; }
+__device__ __forceinline__ float* wo_s(const WOProj& p) { return p.fac + 2 * p.R + 2 * p.C; }
+__device__ __forceinline__ float* wo_bw(const WOProj& p) { return p.bw; }
+
+__global__ void wo_bank_factors_kernel(const WOProj* __restrict__ tab) {
+  const WOProj p = tab[blockIdx.y];
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= p.R + p.C) return;
+  const float vv = p.v[0];
+  if (row < p.R) {
+    const float* wr = p.Wc + (long)row * p.R;
+    float acc = 0.f;
+    for (int j = lane; j < p.R; j += 32) acc += wr[j] * (p.w1[j] * vv + p.b1[j]);
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      wo_a(p)[row] = acc;
+      wo_vx(p)[row] = p.w1[row] * vv + p.b1[row];
+    }
+  } else {
+    const int c = row - p.R;
+    const float* wr = p.Wr + (long)c * p.C;
+    float acc = 0.f, sum = 0.f;
+    for (int j = lane; j < p.C; j += 32) {
+      const float w = wr[j];
+      acc += w * (p.w2[j] * vv + p.b2[j]);
+      sum += w;
+    }
+    acc = warp_sum(acc);
+    sum = warp_sum(sum);
+    if (lane == 0) {
+      wo_b(p)[c] = acc;
+      wo_s(p)[c] = sum;
+      wo_vy(p)[c] = p.w2[c] * vv + p.b2[c];
+    }
+  }
+}
+__global__ void wo_bank_weff_kernel(const WOProj* __restrict__ tab) {
+  const WOProj p = tab[blockIdx.y];
+  const int vpr = p.R / 4;
+  const long n = (long)p.C * vpr;
+  const float* a = wo_a(p);
+  const float* b = wo_b(p);
+  const float* s = wo_s(p);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i / vpr);
+    const int r = (int)(i % vpr) * 4;
+    const float4 w = *reinterpret_cast<const float4*>(p.W + (long)c * p.R + r);
+    const float4 av = *reinterpret_cast<const float4*>(a + r);
+    const float4 bv = *reinterpret_cast<const float4*>(p.bc + r);
+    const float bb = b[c], ss = s[c], one = 1.f + p.br[c];
+    *reinterpret_cast<uint2*>(p.weff + (long)c * p.R + r) =
+        make_uint2(pack_bf16(w.x * (one + bb * av.x + ss * bv.x), w.y * (one + bb * av.y + ss * bv.y)),
+                   pack_bf16(w.z * (one + bb * av.z + ss * bv.z), w.w * (one + bb * av.w + ss * bv.w)));
+  }
+}
+// backward 1: row / column reductions of G = dW_eff ⊙ W  (GTb, GTs pre-zeroed)
+__global__ void __launch_bounds__(256) wo_bank_reduce_kernel(const WOProj* __restrict__ tab) {
+  const WOProj p = tab[blockIdx.y];
+  extern __shared__ float wsm[];  // [2][Rmax]
+  if (blockIdx.x * 8 >= p.C) return;
+  const int R = p.R, C = p.C;
+  float* cb = wsm;
+  float* cs = wsm + R;
+  for (int r = threadIdx.x; r < R; r += blockDim.x) cb[r] = cs[r] = 0.f;
+  __syncthreads();
+  const float* a = wo_a(p);
+  const float* b = wo_b(p);
+  const float* s = wo_s(p);
+  float* bw = wo_bw(p);
+  float *Ga = bw, *Gbc = bw + C, *G1 = bw + 2 * C, *GTb = bw + 3 * C, *GTs = bw + 3 * C + R;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 8 + warp;
+  if (c < C) {
+    const float bcv = b[c], scv = s[c];
+    float ga = 0.f, gbc = 0.f, g1 = 0.f;
+    for (int r = lane; r < R; r += 32) {
+      const float g = p.dweff[(long)c * R + r] * p.W[(long)c * R + r];
+      ga += g * a[r];
+      gbc += g * p.bc[r];
+      g1 += g;
+      atomicAdd(&cb[r], g * bcv);
+      atomicAdd(&cs[r], g * scv);
+    }
+    ga = warp_sum(ga);
+    gbc = warp_sum(gbc);
+    g1 = warp_sum(g1);
+    if (lane == 0) {
+      Ga[c] = ga;
+      Gbc[c] = gbc;
+      G1[c] = g1;
+    }
+  }
+  __syncthreads();
+  for (int r = threadIdx.x; r < R; r += blockDim.x) {
+    atomicAdd(&GTb[r], cb[r]);
+    atomicAdd(&GTs[r], cs[r]);
+  }
+}
+// backward 2: dvy = Wrᵀ Ga, dvx = Wcᵀ GTb (column mat-vecs; dvx/dvy pre-zeroed).  blockIdx.z = 2*proj + which
+__global__ void wo_bank_colmatvec_kernel(const WOProj* __restrict__ tab) {
+  const WOProj p = tab[blockIdx.z >> 1];
+  const int which = blockIdx.z & 1;  // 0: Wr/Ga -> dvy (n = C), 1: Wc/GTb -> dvx (n = R)
+  const int n = which == 0 ? p.C : p.R;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i0 = blockIdx.y * 32;
+  if (j >= n || i0 >= n) return;
+  float* bw = wo_bw(p);
+  const float* M = which == 0 ? p.Wr : p.Wc;
+  const float* x = which == 0 ? bw : bw + 3 * p.C;
+  float* out = which == 0 ? bw + 3 * p.C + 3 * p.R : bw + 3 * p.C + 2 * p.R;
+  float acc = 0.f;
+  const int i1 = min(n, i0 + 32);
+#pragma unroll 8
+  for (int i = i0; i < i1; ++i) acc += M[(long)i * n + j] * x[i];
+  atomicAdd(&out[j], acc);
+}
+// backward 3: dWr = Ga vyᵀ + Gbc 1ᵀ, dWc = GTb vxᵀ.  blockIdx.y = 2*proj + which
+__global__ void wo_bank_outer_kernel(const WOProj* __restrict__ tab) {
+  const WOProj p = tab[blockIdx.y >> 1];
+  const int which = blockIdx.y & 1;
+  float* bw = wo_bw(p);
+  const int n = which == 0 ? p.C : p.R;
+  const float* u = which == 0 ? bw : bw + 3 * p.C;                 // Ga | GTb
+  const float* w = which == 0 ? wo_vy(p) : wo_vx(p);
+  const float* t = which == 0 ? bw + p.C : nullptr;               // Gbc
+  float* dM = which == 0 ? p.dWr : p.dWc;
+  const long total = (long)n * n / 4;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int r = (int)((i * 4) / n), c = (int)((i * 4) % n);
+    const float ur = u[r], tr = t ? t[r] : 0.f;
+    const float4 wv = *reinterpret_cast<const float4*>(w + c);
+    *reinterpret_cast<float4*>(dM + i * 4) = make_float4(ur * wv.x + tr, ur * wv.y + tr, ur * wv.z + tr, ur * wv.w + tr);
+  }
+}
+// backward 4: vector grads (dw1, db1, dw2, db2, dv) and the copies dbr = G1, dbc = GTs.  one block per projection
+__global__ void wo_bank_vec_kernel(const WOProj* __restrict__ tab) {
+  const WOProj p = tab[blockIdx.x];
+  __shared__ float red[32];
+  const int R = p.R, C = p.C;
+  float* bw = wo_bw(p);
+  const float *G1 = bw + 2 * C, *GTs = bw + 3 * C + R, *dvx = bw + 3 * C + 2 * R, *dvy = bw + 3 * C + 3 * R;
+  const float vv = p.v[0];
+  float acc = 0.f;
+  for (int j = threadIdx.x; j < R; j += blockDim.x) {
+    const float d = dvx[j];
+    p.dw1[j] = d * vv;
+    p.db1[j] = d;
+    p.dbc[j] = GTs[j];
+    acc += p.w1[j] * d;
+  }
+  for (int j = threadIdx.x; j < C; j += blockDim.x) {
+    const float d = dvy[j];
+    p.dw2[j] = d * vv;
+    p.db2[j] = d;
+    p.dbr[j] = G1[j];
+    acc += p.w2[j] * d;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) p.dv[0] = t;
+  }
+}
+// tab: device array of n WOProj records; max_r / max_c: largest row/column dims in the bank.
+extern "C" int e4t_wo_bank_fwd(const void* tab, int n, int max_r, int max_c, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  const WOProj* t = (const WOProj*)tab;
+  wo_bank_factors_kernel<<<dim3(cdiv(max_r + max_c, 8), n), 256, 0, st>>>(t);
+  E4T_COUNT_LAUNCH();
+  wo_bank_weff_kernel<<<dim3(cdiv((long)max_r * max_c / 4, 256 * 4), n), 256, 0, st>>>(t);
+  E4T_COUNT_LAUNCH();
+  E4T_LAUNCH_CHECK();
+  return 0;
+}
+// fac_bw: pointer to the start of the (contiguous) factor scratch of the whole bank and its size in floats: the
+// backward sub-ranges that need zeroing (GTb, GTs, dvx, dvy) are zeroed by clearing every projection's backward area.
+extern "C" int e4t_wo_bank_bwd(const void* tab, int n, int max_r, int max_c, float* bw_base, long long bw_floats,
+                               void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  const WOProj* t = (const WOProj*)tab;
+  E4T_CUDA(cudaMemsetAsync(bw_base, 0, (size_t)bw_floats * sizeof(float), st));
+  wo_bank_reduce_kernel<<<dim3(cdiv(max_c, 8), n), 256, (size_t)2 * max_r * sizeof(float), st>>>(t);
+  E4T_COUNT_LAUNCH();
+  const int mx = max_r > max_c ? max_r : max_c;
+  wo_bank_colmatvec_kernel<<<dim3(cdiv(mx, 128), cdiv(mx, 32), 2 * n), 128, 0, st>>>(t);
+  E4T_COUNT_LAUNCH();
+  wo_bank_outer_kernel<<<dim3(cdiv((long)mx * mx / 4, 256 * 4), 2 * n), 256, 0, st>>>(t);
+  E4T_COUNT_LAUNCH();
+  wo_bank_vec_kernel<<<n, 256, 0, st>>>(t);
+  E4T_COUNT_LAUNCH();
+  E4T_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int e4t_wo_bank_record_size(void) { return (int)sizeof(WOProj); }

@@ -48,6 +48,18 @@ class CrossAttention(nn.Module):
         self.wo_k = WeightOffsets(cross_attention_dim, inner_dim)
         self.wo_v = WeightOffsets(cross_attention_dim, inner_dim)
         self._weff_cache = {}
+        self._wo_bank = None      # set by e4t_b200.wobank (batched WeightOffsets kernels across the whole UNet)
+
+    def _project(self, x, group):
+        """x @ W_eff(group)ᵀ with the WeightOffsets-modulated, row-concatenated projection weights."""
+        bank = self._wo_bank
+        if bank is not None:
+            w_eff, dweff, token = bank.get(self, group)
+            if token is not None:
+                return FN.WOLinearBankFn.apply(x, w_eff, dweff, token)
+            return FN.LinearFn.apply(x, w_eff, None, None)
+        w_eff, carrier = self.effective_weights(group)
+        return FN.WOLinearFn.apply(x, w_eff, carrier)
 
     # ---- API kept for the training scripts (pretrain_e4t.py:264-272) -------------------------
     def set_use_memory_efficient_attention_xformers(self, use, attention_op=None):
@@ -115,15 +127,12 @@ class B200AttnProcessor:
             raise E4TError("e4t CrossAttention runs on the sm_100a kernels only (no CPU fallback)")
         x = FN.as_bf16(hidden_states)
         if encoder_hidden_states is None:
-            w_eff, carrier = attn.effective_weights("qkv")
-            qkv = FN.WOLinearFn.apply(x, w_eff, carrier)
+            qkv = attn._project(x, "qkv")
             o = FN.AttentionFn.apply(qkv, None, attn.heads, attn.scale)
         else:
             ctx = FN.as_bf16(encoder_hidden_states)
-            wq, cq = attn.effective_weights("q")
-            wkv, ckv = attn.effective_weights("kv")
-            q = FN.WOLinearFn.apply(x, wq, cq)
-            kv = FN.WOLinearFn.apply(ctx, wkv, ckv)
+            q = attn._project(x, "q")
+            kv = attn._project(ctx, "kv")
             o = FN.AttentionFn.apply(q, kv, attn.heads, attn.scale)
         out = attn.to_out[0]
         y = FN.LinearFn.apply(o, _weight_bf16(out), out.bias, residual)

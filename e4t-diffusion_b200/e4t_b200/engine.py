@@ -141,6 +141,14 @@ class PretrainStep:
         self.opt = FlatAdamW(trainable_parameters(unet, e4t_encoder), lr=lr, betas=betas, weight_decay=weight_decay,
                              eps=eps) if optimizer else None
         self._graph = None
+        self.wo_bank = None
+        if self.opt is not None:
+            from .wobank import WOBank
+            from e4t.models.cross_attention import CrossAttention
+            attns = [m for m in unet.modules() if isinstance(m, CrossAttention)]
+            self.wo_bank = WOBank(attns)
+            for m in attns:
+                m._wo_bank = self.wo_bank
 
     def placeholder_idxs(self, input_ids):
         """[ids.index(placeholder_id) for ids in input_ids] (pretrain_e4t.py:617) — exact integer bookkeeping."""
@@ -210,6 +218,8 @@ class PretrainStep:
         return self
 
     def _drop_autograd_refs(self):
+        if self.wo_bank is not None:
+            self.wo_bank.drop_autograd_refs()
         for m in self.unet.modules():
             c = getattr(m, "_weff_cache", None)
             if c is not None:

@@ -107,6 +107,33 @@ class WOLinearFn(torch.autograd.Function):
         return dx, None, dw
 
 
+class WOLinearBankFn(torch.autograd.Function):
+    """WOLinearFn for projections managed by a wobank.WOBank: the weight gradient is accumulated (fp32 atomics of the
+    split-K GEMM) straight into the bank's dW_eff buffer; `token` only orders the bank's backward after this node."""
+
+    @staticmethod
+    def forward(ctx, x, w_eff, dweff, token):
+        shp = x.shape
+        x2 = _c(x).view(-1, shp[-1])
+        y = ops.gemm(x2, w_eff)
+        ctx.save_for_backward(x2, w_eff)
+        ctx.dweff = dweff
+        ctx.shp = shp
+        return y.view(*shp[:-1], w_eff.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w_eff = ctx.saved_tensors
+        C, R = w_eff.shape
+        dy2 = _c(dy).view(-1, C)
+        dx = ops.gemm(dy2, w_eff, b_mn=True).view(ctx.shp) if ctx.needs_input_grad[0] else None
+        m = x2.shape[0]
+        tiles = ((C + 127) // 128) * ((R + 127) // 128)
+        splits = max(1, min((m + 63) // 64, (2 * 148 + tiles - 1) // tiles))
+        ops.gemm(dy2, x2, a_mn=True, b_mn=True, out=ctx.dweff, accumulate=True, splits=splits)
+        return dx, None, None, None
+
+
 class Conv3x3Fn(torch.autograd.Function):
     """3x3/s1/p1 convolution on NHWC (+bias +per-image row add (time embedding) +residual).  Backward: dX via the same
     implicit-GEMM kernel with the flipped/transposed taps; pass-through to residual."""

@@ -114,6 +114,13 @@ int e4t_wo_bwd(const float* dWeff, const float* W, const float* v, const float* 
                const float* s, float* scratch, float* dv, float* dw1, float* db1, float* dw2, float* db2, float* dWc,
                float* dbc, float* dWr, float* dbr, int R, int C, void* stream);
 
+/* Batched variants over ALL WeightOffsets projections of a model: `tab` is a device array of n WOProj records
+ * (csrc/elementwise.cu; mirrored by e4t_b200/wobank.py) holding parameter, scratch, W_eff, dW_eff and gradient
+ * pointers.  fwd = 2 launches (factors, W_eff); bwd = 4 launches + one memset of the backward scratch. */
+int e4t_wo_bank_fwd(const void* tab, int n, int max_r, int max_c, void* stream);
+int e4t_wo_bank_bwd(const void* tab, int n, int max_r, int max_c, float* bw_base, long long bw_floats, void* stream);
+int e4t_wo_bank_record_size(void);
+
 /* ---- optimiser (torch.optim.AdamW at pretrain_e4t.py:389-392,652) ---------------------------------------------- */
 int e4t_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                    float eps, float weight_decay, int step, float grad_scale, void* stream);
