@@ -218,7 +218,8 @@ def micro_rooflines(B, peaks, device):
 # ------------------------------------------------------------------------------------------------------------------
 def cpu_oracle_setup():
     from oracle import e4t_oracle as O
-    torch.set_num_threads(os.cpu_count())
+    # more threads than ~32 only add synchronisation overhead to these (small-batch) CPU GEMMs/convs
+    torch.set_num_threads(min(os.cpu_count(), 32))
     g = torch.Generator().manual_seed(0)
 
     def rnd_sd(shapes):
@@ -263,8 +264,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count()
     state = cpu_oracle_setup()
+    cores = torch.get_num_threads()
     B = 1
     t_w, _ = cpu_oracle_step(state, B, 1)                     # warm-up (also sizes the run)
     budget = 200.0
@@ -277,7 +278,7 @@ def run_reference(args):
     val = B * steps / tot
     sample = (f"{steps} timed step(s) (of {args.steps} requested; capped to ~{int(budget)} s of CPU work) of the full "
               f"pre-training step at B={B} image/step, SD-v1.4 UNet + ViT-H/14 + CLIP-L text, fp32, "
-              f"torch.set_num_threads({cores}); 1 warm-up step")
+              f"torch.set_num_threads({cores}) of {os.cpu_count()} host cores; 1 warm-up step")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "images/sec", "n_gpus": args.gpus,
             "steps": steps, "warmup": 1, "ms_per_step": tot / steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -409,7 +410,7 @@ def main():
         try:
             state = cpu_oracle_setup()
             t_cpu, _ = cpu_oracle_step(state, 1, 1)
-            cpu = {"value": 1.0 / t_cpu, "unit": "images/sec", "cores": os.cpu_count(), "kind": "port",
+            cpu = {"value": 1.0 / t_cpu, "unit": "images/sec", "cores": torch.get_num_threads(), "kind": "port",
                    "sample": "ONE full pre-training step at B=1 image (SD-v1.4 UNet x2 fwd + ViT-H/14 + CLIP-L text + "
                              "bwd + AdamW), fp32 CPU oracle (oracle/e4t_oracle.py), all host threads, no warm-up"}
             del state
