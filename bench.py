@@ -187,8 +187,8 @@ def micro_rooflines(B, peaks, device):
     o, lse = ops.attn_fwd(q, k, v, H)
     do = torch.randn_like(o)
     t = timeit(lambda: ops.attn_bwd(q, k, v, o, do, lse, H))
-    res["attn_bwd_L0_self"] = dict(ms=t * 1e3, tflops=2.5 * fl / t / 1e12, flops=2.5 * fl,
-                                   note="algorithmic 2.5x fwd (recompute excluded)")
+    res["attn_bwd_fused_L0_self"] = dict(ms=t * 1e3, tflops=2.5 * fl / t / 1e12, flops=2.5 * fl,
+                                         note="algorithmic 2.5x fwd (recompute excluded)")
     # (2) fused WO-modulated QKV projection GEMM, level 0: (B*4096, 320) x (960, 320)^T
     x = (torch.randn(B * N, C, device=device, generator=g)).to(torch.bfloat16)
     w = (torch.randn(3 * C, C, device=device, generator=g) * 0.05).to(torch.bfloat16)
