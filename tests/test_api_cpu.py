@@ -102,3 +102,39 @@ def test_attribute_dict_and_checkpoint_filters(tmp_path):
     (tmp_path / "config.json").write_text(json.dumps({"pretrained_model_name_or_path": "x", "reg_lambda": 0.01}))
     cfg = load_config_from_pretrained(str(tmp_path))
     assert cfg.reg_lambda == 0.01 and cfg.not_there is None and isinstance(cfg, AttributeDict)
+
+
+def test_wo_bank_record_layout_matches_library():
+    """The ctypes mirror of the device table record (e4t_b200/wobank.py) matches csrc/elementwise.cu's WOProj."""
+    from e4t_b200 import _lib
+    from e4t_b200.wobank import _WOProj
+    lib = _lib.load()
+    lib.e4t_wo_bank_record_size.restype = ctypes.c_int
+    assert lib.e4t_wo_bank_record_size() == ctypes.sizeof(_WOProj) == 23 * 8 + 8
+
+
+@pytest.mark.parametrize("R,C", [(8, 8), (24, 16), (40, 72)])
+def test_wo_closed_form_gradients_match_autograd(R, C):
+    """SURVEY.md Appendix A backward identities (what wo_bank_*_kernel implement) vs autograd of the literal module."""
+    torch.manual_seed(R * 100 + C)
+    sd = {k: torch.randn(s, dtype=torch.float64) for k, s in O._wo_shapes("p.", R, C).items()}
+    for v in sd.values():
+        v.requires_grad_(True)
+    W = torch.randn(C, R, dtype=torch.float64)
+    dWeff = torch.randn(C, R, dtype=torch.float64)
+    ((W * (1 + O.wo_delta(sd, "p."))) * dWeff).sum().backward()
+    with torch.no_grad():
+        v, w1, b1 = sd["p.v"], sd["p.linear1.weight"][:, 0], sd["p.linear1.bias"]
+        w2, b2 = sd["p.linear2.weight"][:, 0], sd["p.linear2.bias"]
+        Wc, bc, Wr = sd["p.linear_column.weight"], sd["p.linear_column.bias"], sd["p.linear_row.weight"]
+        vx, vy = w1 * v + b1, w2 * v + b2
+        a, b, s = Wc @ vx, Wr @ vy, Wr.sum(1)
+        G = dWeff * W
+        Ga, Gbc, G1, GTb, GTs = G @ a, G @ bc, G.sum(1), G.t() @ b, G.t() @ s
+        dvy, dvx = Wr.t() @ Ga, Wc.t() @ GTb
+        exp = {"p.linear_row.weight": Ga[:, None] * vy[None, :] + Gbc[:, None], "p.linear_row.bias": G1,
+               "p.linear_column.weight": GTb[:, None] * vx[None, :], "p.linear_column.bias": GTs,
+               "p.linear2.weight": (dvy * v)[:, None], "p.linear2.bias": dvy, "p.linear1.weight": (dvx * v)[:, None],
+               "p.linear1.bias": dvx, "p.v": (w1 @ dvx + w2 @ dvy).reshape(1)}
+    for k, e in exp.items():
+        assert torch.allclose(sd[k].grad, e, rtol=1e-10, atol=1e-10), k
