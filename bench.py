@@ -433,6 +433,7 @@ def main():
                 "cpu_baseline": cpu}
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()      # rank 0 may still be timing kernels for the roofline object; leave together
         dist.destroy_process_group()
 
 
