@@ -85,8 +85,8 @@ e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
   const long total_tiles = (long)g.batch * g.splits * g.m_tiles * g.n_tiles;
 
   if (warp == 0) {
-    // ===================== TMA producer (one thread) =====================
-    if (lane == 0) {
+    // ===================== TMA producer (whole warp runs the control flow, one elected lane issues) ============
+    {
       int s = 0;
       uint32_t ph = 0;
       for (long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -109,6 +109,7 @@ e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
           mbar_wait(&empty_bar[s], ph ^ 1u);
           uint8_t* sA = smem + (size_t)s * stage_bytes;
           uint8_t* sB = sA + kATileBytes;
+          if (elect_one()) {
           mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
           if (g.conv) {
             const int tap = kc / g.cin_chunks, cc = kc % g.cin_chunks;
@@ -130,6 +131,8 @@ e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 tma_load_3d(sB + i * 8192, &mapB, &full_bar[s], n0 + 64 * i, kc * kBK, bb);
             }
           }
+          }  // elect_one
+          __syncwarp();
           if (++s == g.stages) {
             s = 0;
             ph ^= 1u;
@@ -138,9 +141,17 @@ e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (whole warp runs the control flow, one elected lane issues) ==============
+    {
       const uint32_t idesc = umma_idesc_bf16((uint32_t)g.BN, g.a_mn != 0, g.b_mn != 0);
+      // descriptors of stage 0 / k-step 0; a later stage or k-step only moves the 14-bit start-address field
+      // (all of shared memory is below 256 KiB, so the addition never carries out of the field)
+      const uint32_t s0 = smem_u32(smem);
+      const uint64_t dA0 = g.a_mn ? umma_desc(s0, 8192, 1024) : umma_desc(s0, 16, 1024);
+      const uint64_t dB0 = g.b_mn ? umma_desc(s0 + kATileBytes, 8192, 1024) : umma_desc(s0 + kATileBytes, 16, 1024);
+      const uint32_t a_step = g.a_mn ? (2048u >> 4) : (32u >> 4);
+      const uint32_t b_step = g.b_mn ? (2048u >> 4) : (32u >> 4);
+      const uint32_t stage_units = (uint32_t)stage_bytes >> 4;
       int s = 0, as = 0;
       uint32_t ph = 0, aph = 0;
       for (long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -154,21 +165,23 @@ e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         for (int kc = kc0; kc < kc1; ++kc) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          const uint32_t sA = smem_u32(smem + (size_t)s * stage_bytes);
-          const uint32_t sB = sA + kATileBytes;
+          if (elect_one()) {
+            const uint64_t da = dA0 + (uint64_t)((uint32_t)s * stage_units);
+            const uint64_t db = dB0 + (uint64_t)((uint32_t)s * stage_units);
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            const uint64_t da = g.a_mn ? umma_desc(sA + k * 2048, 8192, 1024) : umma_desc(sA + k * 32, 16, 1024);
-            const uint64_t db = g.b_mn ? umma_desc(sB + k * 2048, 8192, 1024) : umma_desc(sB + k * 32, 16, 1024);
-            umma_bf16(d_tmem, da, db, idesc, (kc > kc0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < kBK / 16; ++k)
+              umma_bf16(d_tmem, da + (uint64_t)(k * a_step), db + (uint64_t)(k * b_step), idesc,
+                        (kc > kc0 || k > 0) ? 1u : 0u);
+            umma_commit(&empty_bar[s]);  // frees the smem stage when these MMAs retire
           }
-          umma_commit(&empty_bar[s]);  // frees the smem stage when these MMAs retire
+          __syncwarp();
           if (++s == g.stages) {
             s = 0;
             ph ^= 1u;
           }
         }
-        umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
+        if (elect_one()) umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
+        __syncwarp();
         as ^= 1;
         if (as == 0) aph ^= 1u;
       }
@@ -200,7 +213,7 @@ e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       if (g.debug & 1) {
       } else if (g.tma_store) {
         // ---- bf16 output: registers -> swizzled smem slab -> TMA store (full-line coalesced writes) ----
-        const bool leader = (threadIdx.x == 128 + 128 * half);
+        const bool lead_warp = (ew == 0);   // warp-uniform; its elected lane owns this half's TMA-store bulk groups
         const uint32_t sw = ((uint32_t)row >> 1) & 3u;
         uint32_t v[32];
         int c = 32 * half;
@@ -253,7 +266,9 @@ e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
           if (g.debug & 4) continue;
           // this half cycles through staging slabs {half, half + 2}
           uint8_t* slab = stage_c + (half + 2 * (slab_ctr & 1)) * 8192;
-          if (leader) tma_store_wait_read<1>();  // the store that last read this slab has drained
+          if (lead_warp) {
+            if (elect_one()) tma_store_wait_read<1>();  // the store that last read this slab has drained
+          }
           if (half == 0) asm volatile("bar.sync 3, 128;" ::: "memory");
           else asm volatile("bar.sync 5, 128;" ::: "memory");
 #pragma unroll
@@ -263,9 +278,11 @@ e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
           fence_proxy_async_smem();
           if (half == 0) asm volatile("bar.sync 4, 128;" ::: "memory");
           else asm volatile("bar.sync 6, 128;" ::: "memory");
-          if (leader) {
-            tma_store_3d(&mapC, slab, n0 + c, m_t * kBM, bz);
-            tma_store_commit();
+          if (lead_warp) {
+            if (elect_one()) {
+              tma_store_3d(&mapC, slab, n0 + c, m_t * kBM, bz);
+              tma_store_commit();
+            }
           }
           ++slab_ctr;
         }
@@ -339,7 +356,9 @@ e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       as ^= 1;
       if (as == 0) aph ^= 1u;
     }
-    if (g.tma_store && (threadIdx.x == 128 || threadIdx.x == 256)) tma_store_wait_all();  // smem must outlive the stores
+    if (g.tma_store && (warp == 4 || warp == 8)) {
+      if (elect_one()) tma_store_wait_all();  // smem must outlive the stores (same lane that committed them)
+    }
   }
 
   tc_fence_before();

@@ -1,0 +1,121 @@
+"""Sweep the half-tile ping-pong fused attention backward (E4T_ATTN_PP=1..4) against the default kernel.
+
+    python tools/pp_sweep.py              # parent: one subprocess per mode (a hung variant cannot take the others down)
+    python tools/pp_sweep.py --mode 2     # child: parity vs fp32 torch + the default kernel, then timing at B=16 level 0
+
+Writes gpurun_out/pp_sweep.json and gpurun_out/pp_best.txt (0 = keep the default kernel).
+"""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "gpurun_out")
+
+
+def child(mode):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "e4t-diffusion_b200")]
+    import torch
+    from e4t_b200 import ops
+
+    dev = "cuda"
+
+    def mk(shape, g, s=0.5):
+        return (torch.randn(*shape, device=dev, generator=g) * s).to(torch.bfloat16)
+
+    def rel(a, b):
+        a, b = a.float(), b.float()
+        return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+    def ref(q, k, v, do, H):
+        B, N, C = q.shape
+        dh = C // H
+        qr, kr, vr = (t.float().requires_grad_(True) for t in (q, k, v))
+        qh = qr.view(B, N, H, dh).transpose(1, 2)
+        kh = kr.view(B, -1, H, dh).transpose(1, 2)
+        vh = vr.view(B, -1, H, dh).transpose(1, 2)
+        s = (qh @ kh.transpose(-1, -2)) * dh ** -0.5
+        o = (s.softmax(-1) @ vh).transpose(1, 2).reshape(B, N, C)
+        o.backward(do.float())
+        return qr.grad, kr.grad, vr.grad
+
+    res = {"mode": mode, "parity": {}, "ok": True}
+    shapes = [(2, 8, 256, 256, 40), (2, 8, 1024, 77, 40), (2, 4, 256, 256, 16), (1, 8, 300, 200, 40),
+              (1, 4, 384, 128, 64), (1, 8, 4096, 4096, 40)]
+    for (B, H, N, M, dh) in shapes:
+        g = torch.Generator(device=dev).manual_seed(N + M + dh)
+        C = H * dh
+        q, k, v, do = mk((B, N, C), g), mk((B, M, C), g), mk((B, M, C), g), mk((B, N, C), g)
+        gq, gk, gv = ref(q, k, v, do, H)
+        os.environ["E4T_ATTN_PP"] = "0"
+        o, lse = ops.attn_fwd(q, k, v, H)
+        os.environ["E4T_ATTN_PP"] = str(mode)
+        dq, dk, dv = ops.attn_bwd(q, k, v, o, do, lse, H, fused=True)
+        torch.cuda.synchronize()
+        errs = (rel(dq, gq), rel(dk, gk), rel(dv, gv))
+        res["parity"][f"{B}x{H}x{N}x{M}x{dh}"] = errs
+        if not all(e < 1e-2 for e in errs):
+            res["ok"] = False
+    # timing, level-0 self-attention at the bench batch
+    B, H, N, dh = 16, 8, 4096, 40
+    g = torch.Generator(device=dev).manual_seed(1)
+    C = H * dh
+    q, k, v, do = mk((B, N, C), g), mk((B, N, C), g), mk((B, N, C), g), mk((B, N, C), g, 1.0)
+    o, lse = ops.attn_fwd(q, k, v, H)
+
+    def timeit(m, iters=8):
+        os.environ["E4T_ATTN_PP"] = str(m)
+        for _ in range(2):
+            ops.attn_bwd(q, k, v, o, do, lse, H, fused=True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(iters):
+            ops.attn_bwd(q, k, v, o, do, lse, H, fused=True)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    res["ms_default"] = timeit(0)
+    res["ms_mode"] = timeit(mode)
+    # level-1-like shape with dh=64 (only reachable through the C-ABI; the UNet has 40/80/160)
+    print(json.dumps(res))
+
+
+def parent():
+    os.makedirs(OUT, exist_ok=True)
+    modes = [int(m) for m in os.environ.get("PP_MODES", "1,2,4").split(",")]
+    allres, best, best_ms = [], 0, None
+    subprocess.run([sys.executable, "-c", "import torch"], timeout=300)   # page the image in once, untimed
+    for m in modes:
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--mode", str(m)], capture_output=True,
+                               text=True, timeout=int(os.environ.get("PP_TIMEOUT", "60")))
+            line = [l for l in r.stdout.splitlines() if l.startswith("{")]
+            if r.returncode != 0 or not line:
+                allres.append({"mode": m, "ok": False, "rc": r.returncode, "stderr": r.stderr[-1500:]})
+                continue
+            res = json.loads(line[-1])
+        except subprocess.TimeoutExpired:
+            allres.append({"mode": m, "ok": False, "error": "timeout (hang?)"})
+            continue
+        allres.append(res)
+        if best_ms is None:
+            best_ms = res["ms_default"]
+        if res["ok"] and res["ms_mode"] < 0.97 * res["ms_default"] and res["ms_mode"] < best_ms:
+            best, best_ms = m, res["ms_mode"]
+    with open(os.path.join(OUT, "pp_sweep.json"), "w") as f:
+        json.dump(allres, f, indent=1)
+    with open(os.path.join(OUT, "pp_best.txt"), "w") as f:
+        f.write(str(best))
+    for r in allres:
+        print(json.dumps(r))
+    print("best mode:", best)
+
+
+if __name__ == "__main__":
+    if len(sys.argv) >= 3 and sys.argv[1] == "--mode":
+        child(int(sys.argv[2]))
+    else:
+        parent()
