@@ -911,11 +911,15 @@ __device__ __forceinline__ void mma_ds_k(uint32_t d_tmem, uint32_t sdST, uint32_
               ks > 0 ? 1u : 0u);
 }
 
-template <int CG>
+// DQTMA (opt-in, dh <= 64): dQ_blk is staged in shared memory (fp32 [128][dh], double buffered) and reduced into the
+// accumulator by warp 3 with ONE cp.reduce.async.bulk.tensor per block (full 128-byte lines through the TMA engine)
+// instead of 4 red.global.add.v4.f32 per thread whose lanes each touch their own line (32 LSU wavefronts per warp
+// instruction; 56 % of the kernel's LSU wavefronts in the round-1 ncu capture).
+template <int CG, bool DQTMA>
 __global__ void __launch_bounds__(128 + 128 * CG, 1)
 attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                       const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapdO,
-                      const AttnArgs a, float* __restrict__ dQacc) {
+                      const __grid_constant__ CUtensorMap mapDQ, const AttnArgs a, float* __restrict__ dQacc) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr int BQ = 128;
@@ -927,7 +931,9 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
   uint8_t* sdO = sQ + a.kst * q_tile;
   uint8_t* sPT = sdO + a.kst * q_tile;  // 2 x 16 KiB
   uint8_t* sdST = sPT + 32768;          // 2 x 16 KiB
-  float* sLSE = reinterpret_cast<float*>(sdST + 32768);  // [128]
+  const int dq_tile = DQTMA ? BQ * a.dh * 4 : 0;          // fp32 [128][dh] staging tile of dQ_blk (x2)
+  uint8_t* sDQ = sdST + 32768;
+  float* sLSE = reinterpret_cast<float*>(sdST + 32768 + 2 * dq_tile);  // [128]
   float* sD = sLSE + 128;                                // [128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sD + 128);
   uint64_t* kv_full = bars;
@@ -938,7 +944,9 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
   uint64_t* acc_done = bars + 7;
   uint64_t* dq_full = bars + 8;
   uint64_t* dq_empty = bars + 9;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* dq_staged = bars + 10;  // [2] DQTMA: every thread's part of the staging tile is in shared memory
+  uint64_t* dq_free = bars + 12;    // [2] DQTMA: the TMA reduce has read the staging tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
@@ -947,6 +955,8 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
     for (int i = 0; i < 2; ++i) {
       mbar_init(&q_full[i], 1);
       mbar_init(&q_empty[i], 1);
+      mbar_init(&dq_staged[i], 128 * CG);
+      mbar_init(&dq_free[i], 1);
     }
     mbar_init(sp_full, 1);
     mbar_init(ds_ready, 128 * CG);
@@ -1017,6 +1027,22 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
         }
       }
     }
+  } else if (warp == 3) {
+    if constexpr (DQTMA) {   // dQ store warp: one TMA reduce-add per query block
+      for (int jb = 0; jb < a.nblk; ++jb) {
+        const int buf = jb & 1;
+        mbar_wait(&dq_staged[buf], (uint32_t)((jb >> 1) & 1));
+        if (elect_one()) {
+          tma_reduce_add_3d(&mapDQ, sDQ + buf * dq_tile, h * a.dh, jb * BQ, b);
+          tma_store_commit();
+          tma_store_wait_read<0>();   // the engine has read the tile: the threads may overwrite it
+          mbar_arrive(&dq_free[buf]);
+        }
+        __syncwarp();
+      }
+      if (elect_one()) tma_store_wait_all();
+      __syncwarp();
+    }
   } else if (warp >= 4) {
     constexpr int NSOFT = 128 * CG;
     const int ew = (warp - 4) & 3;
@@ -1037,18 +1063,38 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
       mbar_wait(dq_full, (uint32_t)(jb & 1));
       tc_fence_after();
       const int qn = jb * BQ + row;
-      float* dst = dQacc + ((long long)b * a.N + qn) * C + h * a.dh;
-      for (int oc = cg; oc < ochunk; oc += CG) {
-        uint32_t v[16];
-        __syncwarp();
-        tmem_ld16(tdQ + lane_base + (uint32_t)(oc * 16), v);
-        tmem_ld_wait();
-        if (qn < a.N) {
+      if constexpr (DQTMA) {
+        const int buf = jb & 1;
+        if (jb >= 2) mbar_wait(&dq_free[buf], (uint32_t)(((jb >> 1) - 1) & 1));  // reduce of block jb-2 has read it
+        float* srow = reinterpret_cast<float*>(sDQ + buf * dq_tile) + row * a.dh;
+        for (int oc = cg; oc < ochunk; oc += CG) {
+          uint32_t v[16];
+          __syncwarp();
+          tmem_ld16(tdQ + lane_base + (uint32_t)(oc * 16), v);
+          tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < 16; i += 4)
-            if (oc * 16 + i < a.dh)
-              red_add_v4(dst + oc * 16 + i, __uint_as_float(v[i]), __uint_as_float(v[i + 1]),
-                         __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+            if (oc * 16 + i < a.dh)   // rows past N are clipped by the tensor map
+              *reinterpret_cast<float4*>(srow + oc * 16 + i) =
+                  make_float4(__uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
+                              __uint_as_float(v[i + 3]));
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&dq_staged[buf]);
+      } else {
+        float* dst = dQacc + ((long long)b * a.N + qn) * C + h * a.dh;
+        for (int oc = cg; oc < ochunk; oc += CG) {
+          uint32_t v[16];
+          __syncwarp();
+          tmem_ld16(tdQ + lane_base + (uint32_t)(oc * 16), v);
+          tmem_ld_wait();
+          if (qn < a.N) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4)
+              if (oc * 16 + i < a.dh)
+                red_add_v4(dst + oc * 16 + i, __uint_as_float(v[i]), __uint_as_float(v[i + 1]),
+                           __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+          }
         }
       }
       tc_fence_before();
@@ -1661,8 +1707,9 @@ extern "C" int e4t_attn_bwd_fused(const void* Q, const void* K, const void* V, c
   E4T_CUDA(cudaMemsetAsync(dQacc, 0, (size_t)nacc * sizeof(float), st));
   static bool attr = false;
   if (!attr) {
-    E4T_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    E4T_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    E4T_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    E4T_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    E4T_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     E4T_CUDA(cudaFuncSetAttribute(attn_bwd_fused_pp_kernel<4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     E4T_CUDA(cudaFuncSetAttribute(attn_bwd_fused_pp_kernel<2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     E4T_CUDA(cudaFuncSetAttribute(attn_bwd_fused_pp_kernel<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -1691,6 +1738,17 @@ extern "C" int e4t_attn_bwd_fused(const void* Q, const void* K, const void* V, c
   const size_t smem = fixed + a.kst * per_stage;
   E4T_CHECK(smem <= 227 * 1024, "e4t_attn_bwd_fused: smem budget exceeded (%zu)", smem);
   const int pp = (a.DC == 1 && a.nblk >= 2) ? attn_pp_mode() : 0;
+  // opt-in: dQ through a TMA reduce-add (needs 2 x 128 x dh fp32 of extra shared memory: dh <= 64 only)
+  const char* dqe = getenv("E4T_ATTN_DQ_TMA");
+  const bool dq_tma = !pp && a.DC == 1 && dqe && atoi(dqe) != 0 && smem + (size_t)2 * 128 * dh * 4 <= 227 * 1024;
+  CUtensorMap mDQ;
+  memset(&mDQ, 0, sizeof(mDQ));
+  if (dq_tma) {
+    const uint64_t dims[3] = {(uint64_t)H * dh, (uint64_t)N, (uint64_t)B};
+    const uint64_t str[2] = {(uint64_t)H * dh * 4, (uint64_t)N * H * dh * 4};
+    const uint32_t box[3] = {(uint32_t)dh, 128, 1};
+    if (int e = e4t_tmap_encode(&mDQ, dQacc, 3, dims, str, box, 4, 0)) return e;
+  }
   if (pp) {   // half-tile ping-pong variant: fixed smem map (see the kernel)
     const size_t smem_pp = 32768 + 65536 + 32768 + 65536 + 4096 + 256 + 1024;
     const dim3 grid(cdiv(M, 128), H, B);
@@ -1698,8 +1756,11 @@ extern "C" int e4t_attn_bwd_fused(const void* Q, const void* K, const void* V, c
     else if (pp == 2) attn_bwd_fused_pp_kernel<2, 16><<<grid, 128 + 128 * 2, smem_pp, st>>>(mQ, mK, mV, mdO, a, dQacc);
     else if (pp == 3) attn_bwd_fused_pp_kernel<2, 8><<<grid, 128 + 128 * 2, smem_pp, st>>>(mQ, mK, mV, mdO, a, dQacc);
     else attn_bwd_fused_pp_kernel<4, 16><<<grid, 128 + 128 * 4, smem_pp, st>>>(mQ, mK, mV, mdO, a, dQacc);
-  } else if (attn_cg(1) == 4) attn_bwd_fused_kernel<4><<<dim3(cdiv(M, 128), H, B), 128 + 128 * 4, smem, st>>>(mQ, mK, mV, mdO, a, dQacc);
-  else attn_bwd_fused_kernel<2><<<dim3(cdiv(M, 128), H, B), 128 + 128 * 2, smem, st>>>(mQ, mK, mV, mdO, a, dQacc);
+  } else if (dq_tma) {
+    attn_bwd_fused_kernel<4, true><<<dim3(cdiv(M, 128), H, B), 128 + 128 * 4, smem + 2 * 128 * dh * 4, st>>>(
+        mQ, mK, mV, mdO, mDQ, a, dQacc);
+  } else if (attn_cg(1) == 4) attn_bwd_fused_kernel<4, false><<<dim3(cdiv(M, 128), H, B), 128 + 128 * 4, smem, st>>>(mQ, mK, mV, mdO, mDQ, a, dQacc);
+  else attn_bwd_fused_kernel<2, false><<<dim3(cdiv(M, 128), H, B), 128 + 128 * 2, smem, st>>>(mQ, mK, mV, mdO, mDQ, a, dQacc);
   E4T_COUNT_LAUNCH();
   E4T_LAUNCH_CHECK();
   const long long total_vec = (long long)B * N * (H * dh / 8);

@@ -1,4 +1,5 @@
-"""Sweep the half-tile ping-pong fused attention backward (E4T_ATTN_PP=1..4) against the default kernel.
+"""Sweep the opt-in fused attention backward variants against the default kernel.
+mode = 10*dq + pp:  pp = E4T_ATTN_PP (half-tile ping-pong, 1..4),  dq = E4T_ATTN_DQ_TMA (dQ through a TMA reduce-add).
 
     python tools/pp_sweep.py              # parent: one subprocess per mode (a hung variant cannot take the others down)
     python tools/pp_sweep.py --mode 2     # child: parity vs fp32 torch + the default kernel, then timing at B=16 level 0
@@ -20,6 +21,10 @@ def child(mode):
     from e4t_b200 import ops
 
     dev = "cuda"
+
+    def setmode(m):
+        os.environ["E4T_ATTN_PP"] = str(m % 10)
+        os.environ["E4T_ATTN_DQ_TMA"] = str(m // 10)
 
     def mk(shape, g, s=0.5):
         return (torch.randn(*shape, device=dev, generator=g) * s).to(torch.bfloat16)
@@ -48,9 +53,9 @@ def child(mode):
         C = H * dh
         q, k, v, do = mk((B, N, C), g), mk((B, M, C), g), mk((B, M, C), g), mk((B, N, C), g)
         gq, gk, gv = ref(q, k, v, do, H)
-        os.environ["E4T_ATTN_PP"] = "0"
+        setmode(0)
         o, lse = ops.attn_fwd(q, k, v, H)
-        os.environ["E4T_ATTN_PP"] = str(mode)
+        setmode(mode)
         dq, dk, dv = ops.attn_bwd(q, k, v, o, do, lse, H, fused=True)
         torch.cuda.synchronize()
         errs = (rel(dq, gq), rel(dk, gk), rel(dv, gv))
@@ -65,7 +70,7 @@ def child(mode):
     o, lse = ops.attn_fwd(q, k, v, H)
 
     def timeit(m, iters=8):
-        os.environ["E4T_ATTN_PP"] = str(m)
+        setmode(m)
         for _ in range(2):
             ops.attn_bwd(q, k, v, o, do, lse, H, fused=True)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -79,13 +84,12 @@ def child(mode):
 
     res["ms_default"] = timeit(0)
     res["ms_mode"] = timeit(mode)
-    # level-1-like shape with dh=64 (only reachable through the C-ABI; the UNet has 40/80/160)
     print(json.dumps(res))
 
 
 def parent():
     os.makedirs(OUT, exist_ok=True)
-    modes = [int(m) for m in os.environ.get("PP_MODES", "1,2,4").split(",")]
+    modes = [int(m) for m in os.environ.get("PP_MODES", "10,4,1").split(",")]
     allres, best, best_ms = [], 0, None
     subprocess.run([sys.executable, "-c", "import torch"], timeout=300)   # page the image in once, untimed
     for m in modes:
