@@ -1533,13 +1533,12 @@ static int make_head_map(CUtensorMap* m, const void* p, int dh, int H, int rows,
 static int round16(int x) { return (x + 15) / 16 * 16; }
 // column groups of softmax/dS warps per kernel (0 fwd, 1 dQ, 2 dKV); E4T_ATTN_CG="f,q,k" overrides for tuning
 static int attn_cg(int which) {
-  static int cfg[4] = {0, 0, 0, 1};   // [3]: allow the two-CTAs-per-SM variants
-  if (cfg[0] == 0) {
-    cfg[0] = 4; cfg[1] = 4; cfg[2] = 4;
-    const char* e = getenv("E4T_ATTN_CG");
-    if (e) sscanf(e, "%d,%d,%d,%d", &cfg[0], &cfg[1], &cfg[2], &cfg[3]);
-    for (int i = 0; i < 3; ++i) if (cfg[i] != 2 && cfg[i] != 4) cfg[i] = 4;
-  }
+  // defaults 4,4,4 and two-CTAs-per-SM variants allowed; the environment is parsed on every call (cheap) so a tuning
+  // script can sweep the variants in one process
+  int cfg[4] = {4, 4, 4, 1};
+  const char* e = getenv("E4T_ATTN_CG");
+  if (e) sscanf(e, "%d,%d,%d,%d", &cfg[0], &cfg[1], &cfg[2], &cfg[3]);
+  for (int i = 0; i < 3; ++i) if (cfg[i] != 2 && cfg[i] != 4) cfg[i] = 4;
   return cfg[which];
 }
 

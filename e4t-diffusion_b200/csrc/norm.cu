@@ -4,6 +4,7 @@
 //   LayerNorm          : BasicTransformerBlock.norm1/2/3 (attention.py:258-273)
 // Coalesced 16-byte / 4-byte vector loads, warp-shuffle + shared-memory reductions, grids sized well past 148 SMs.
 #include "common.cuh"
+#include <stdlib.h>
 
 // ---------------------------------------------------------------------------------------------
 // GroupNorm statistics: sums[b][g] = (sum x, sum x^2) over HW x (C/G) elements.   (sums pre-zeroed)
@@ -162,7 +163,14 @@ gn_apply_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, const f
   }
 }
 
+// Tuning overrides (unset = the heuristics below): E4T_GN_ROWS = rows per CTA, E4T_GN_THREADS = target block size.
+static int gn_env(const char* name) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : 0;
+}
 static int gn_rows_per_cta(int B, int HW) {
+  const int forced = gn_env("E4T_GN_ROWS");
+  if (forced > 0) return forced;
   // aim for >= ~8 CTAs per SM overall
   int rows = 64;
   while (rows > 4 && (long)B * cdiv(HW, rows) < 148 * 8) rows >>= 1;
@@ -170,7 +178,9 @@ static int gn_rows_per_cta(int B, int HW) {
 }
 static int gn_block(int C) {
   const int vpr = C / 8;
-  int k = 256 / vpr;
+  int target = gn_env("E4T_GN_THREADS");
+  if (target <= 0 || target > kGNMaxThreads) target = 256;
+  int k = target / vpr;
   if (k < 1) k = 1;
   return vpr * k;
 }
