@@ -127,6 +127,19 @@ def time_gemm_signature(key, bns):
                 res[bn] = timeit(lambda: ops.gemm(A, Bm, force_bn=bn, **kw))
             except Exception as ex:      # a forced width the kernel rejects for this shape
                 res[bn] = f"err: {str(ex)[:80]}"
+        if odt == "bf16" and not (has_b or has_rg or has_res):
+            # opt-in plain epilogue loop (E4T_GEMM_EPI_PLAIN=1): must be bit-identical to the general loop
+            try:
+                y0 = ops.gemm(A, Bm, **kw)
+                os.environ["E4T_GEMM_EPI_PLAIN"] = "1"
+                y1 = ops.gemm(A, Bm, **kw)
+                torch.cuda.synchronize()
+                res["plain"] = timeit(lambda: ops.gemm(A, Bm, **kw))
+                res["plain_equal"] = bool(torch.equal(y0, y1))
+            except Exception as ex:
+                res["plain"] = f"err: {str(ex)[:80]}"
+            finally:
+                os.environ.pop("E4T_GEMM_EPI_PLAIN", None)
         flops = 2.0 * M * N * K * batch
     else:
         _, Bn, H, W, Cin, Cout, odt, has_b, has_rg, has_res = key
@@ -153,11 +166,12 @@ def sweep_gemm():
     for key, cnt in sigs.items():
         res, flops = time_gemm_signature(key, bns)
         t_def = res.get(0)
-        good = {bn: t for bn, t in res.items() if isinstance(t, float)}
+        good = {bn: t for bn, t in res.items() if isinstance(t, float) and isinstance(bn, int)}
         best_bn = min(good, key=good.get) if good else None
         rows.append({"sig": list(key), "calls": cnt, "ms_default": t_def, "tflops_default":
                      (flops / t_def / 1e9) if isinstance(t_def, float) else None, "best_bn": best_bn,
                      "ms_best": good.get(best_bn), "by_bn": {str(k): v for k, v in res.items()},
+                     "ms_plain_epilogue": res.get("plain"), "plain_equal": res.get("plain_equal"),
                      "step_ms_default": cnt * t_def if isinstance(t_def, float) else None,
                      "step_ms_best": cnt * good[best_bn] if good else None})
     rows.sort(key=lambda r: -(r["step_ms_default"] or 0))
@@ -167,7 +181,8 @@ def sweep_gemm():
           f"({time.time()-t0:.0f}s)")
     for r in rows[:25]:
         print(f"  {r['calls']:3d} x {r['ms_default']*1e3 if r['ms_default'] else 0:7.1f} us = {r['step_ms_default'] or 0:6.2f} ms  "
-              f"{r['tflops_default'] or 0:6.0f} TF/s  best bn {r['best_bn']} {((r['ms_best'] or 0)*1e3):7.1f} us  {r['sig']}")
+              f"{r['tflops_default'] or 0:6.0f} TF/s  best bn {r['best_bn']} {((r['ms_best'] or 0)*1e3):7.1f} us  "
+              f"plain-epi {r['ms_plain_epilogue']} eq={r['plain_equal']}  {r['sig']}")
     return {"rows": rows, "sum_default_ms": tot, "sum_best_ms": totb}
 
 
