@@ -462,6 +462,33 @@ __global__ void attn_delta_kernel(const bf16* __restrict__ O, const bf16* __rest
 // dQ kernel: CTA = (128-query tile, head, batch); loops over key blocks.
 //   TMEM: S [0,128) | dP [128,256) | dQ [256, 256+dpad)
 // =============================================================================================
+// Opt-in (E4T_ATTN_DELTA2=1): one THREAD per (b, n, h) instead of one warp (attn_delta_kernel keeps 27 of 32 lanes idle
+// at dh = 40 and reaches 0.66 TB/s).  Consecutive threads read consecutive dh-wide slices of a token row, so the loads of a
+// warp cover one contiguous span; the 4-byte results are scattered (H-strided) but are 2 % of the traffic.
+__global__ void attn_delta2_kernel(const bf16* __restrict__ O, const bf16* __restrict__ dO, float* __restrict__ Dv,
+                                   int B, int H, int N, int dh, long long ldo, long long o_bs, long long lddo,
+                                   long long do_bs) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)B * N * H) return;
+  const int h = (int)(t % H);
+  const int n = (int)((t / H) % N);
+  const int b = (int)(t / ((long long)H * N));
+  const bf16* o = O + b * o_bs + (long long)n * ldo + h * dh;
+  const bf16* d = dO + b * do_bs + (long long)n * lddo + h * dh;
+  float acc = 0.f;
+  for (int v = 0; v < dh / 8; ++v) {
+    const uint4 a = *reinterpret_cast<const uint4*>(o + v * 8);
+    const uint4 c = *reinterpret_cast<const uint4*>(d + v * 8);
+    const uint32_t as[4] = {a.x, a.y, a.z, a.w}, cs[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 x = unpack_bf16(as[i]), y = unpack_bf16(cs[i]);
+      acc += x.x * y.x + x.y * y.y;
+    }
+  }
+  Dv[((long long)b * H + h) * N + n] = acc;
+}
+
 template <int CG, int OCC>
 __global__ void __launch_bounds__(128 + 128 * CG, OCC)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
@@ -1550,6 +1577,17 @@ static int attn_pp_mode() {   // read on every call (cheap) so a tuning script c
   return (mode < 0 || mode > 4) ? 0 : mode;
 }
 
+static void launch_attn_delta(const void* O, const void* dO, float* Dv, int B, int H, int N, int dh, long long ldo,
+                              long long o_bs, long long lddo, long long do_bs, cudaStream_t st) {
+  const char* e = getenv("E4T_ATTN_DELTA2");
+  if (e && atoi(e) != 0)
+    attn_delta2_kernel<<<cdiv((long long)B * N * H, 256), 256, 0, st>>>((const bf16*)O, (const bf16*)dO, Dv, B, H, N, dh,
+                                                                        ldo, o_bs, lddo, do_bs);
+  else
+    attn_delta_kernel<<<cdiv((long long)B * N * H, 8), 256, 0, st>>>((const bf16*)O, (const bf16*)dO, Dv, B, H, N, dh,
+                                                                     ldo, o_bs, lddo, do_bs);
+}
+
 static int attn_common_checks(int dh, long long ldq, long long ldk, long long ldv) {
   E4T_CHECK(dh % 8 == 0 && dh >= 8 && dh <= 192, "attention: head dim %d unsupported (need dh %% 8 == 0, <= 192)", dh);
   E4T_CHECK(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0, "attention: row strides must be multiples of 8 elements");
@@ -1612,8 +1650,7 @@ extern "C" int e4t_attn_bwd(const void* Q, const void* K, const void* V, const v
   cudaStream_t st = (cudaStream_t)stream_;
   if (int e = attn_common_checks(dh, ldq, ldk, ldv)) return e;
   E4T_CHECK(lddo % 8 == 0 && lddq % 8 == 0 && lddk % 8 == 0 && lddv % 8 == 0, "e4t_attn_bwd: strides %% 8");
-  attn_delta_kernel<<<cdiv((long long)B * N * H, 8), 256, 0, st>>>((const bf16*)O, (const bf16*)dO, Dv, B, H, N, dh, ldo,
-                                                                   o_bs, lddo, do_bs);
+  launch_attn_delta(O, dO, Dv, B, H, N, dh, ldo, o_bs, lddo, do_bs, st);
   E4T_COUNT_LAUNCH();
   E4T_LAUNCH_CHECK();
   static bool attr = false;
@@ -1699,8 +1736,7 @@ extern "C" int e4t_attn_bwd_fused(const void* Q, const void* K, const void* V, c
     return e4t_attn_bwd(Q, K, V, O, dO, LSE, Dv, dQ, dK, dV, B, H, N, M, dh, ldq, q_bs, ldk, k_bs, ldv, v_bs, ldo, o_bs,
                         lddo, do_bs, lddq, dq_bs, lddk, dk_bs, lddv, dv_bs, scale, stream_);
   E4T_CHECK(lddo % 8 == 0 && lddq % 8 == 0 && lddk % 8 == 0 && lddv % 8 == 0, "e4t_attn_bwd_fused: strides %% 8");
-  attn_delta_kernel<<<cdiv((long long)B * N * H, 8), 256, 0, st>>>((const bf16*)O, (const bf16*)dO, Dv, B, H, N, dh, ldo,
-                                                                   o_bs, lddo, do_bs);
+  launch_attn_delta(O, dO, Dv, B, H, N, dh, ldo, o_bs, lddo, do_bs, st);
   E4T_COUNT_LAUNCH();
   const long long nacc = (long long)B * N * H * dh;
   E4T_CUDA(cudaMemsetAsync(dQacc, 0, (size_t)nacc * sizeof(float), st));
