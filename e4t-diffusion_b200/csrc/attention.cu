@@ -942,7 +942,10 @@ __device__ __forceinline__ void mma_ds_k(uint32_t d_tmem, uint32_t sdST, uint32_
 // accumulator by warp 3 with ONE cp.reduce.async.bulk.tensor per block (full 128-byte lines through the TMA engine)
 // instead of 4 red.global.add.v4.f32 per thread whose lanes each touch their own line (32 LSU wavefronts per warp
 // instruction; 56 % of the kernel's LSU wavefronts in the round-1 ncu capture).
-template <int CG, bool DQTMA>
+// PT (opt-in, E4T_ATTN_PT_TMEM=1): the threads write Pᵀ into 64 TMEM columns (tcgen05.st) and dV += Pᵀ·dO takes its A
+// operand from TMEM: no Pᵀ stores to shared memory and no 4 KiB A-tile read per N=48 MMA (which is what makes those
+// MMAs shared-memory-bandwidth bound: 5.5 KiB of operands per 24-clk instruction against 128 B/clk).
+template <int CG, bool DQTMA, bool PT>
 __global__ void __launch_bounds__(128 + 128 * CG, 1)
 attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                       const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapdO,
@@ -999,6 +1002,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
   const uint32_t tmem = *tmem_slot;
   const uint32_t tST = tmem, tdPT = tmem + 128, tdV = tmem + 256, tdK = tdV + (uint32_t)a.dpad,
                  tdQ = tdK + (uint32_t)a.dpad;
+  const uint32_t tPT = tdQ + (uint32_t)a.dpad;   // PT: Pᵀ as bf16 pairs, 64 columns (256 + 3*dpad + 64 <= 512)
 
   if (warp == 0) {   // whole warp runs the control flow, one elected lane issues (see attn_fwd_kernel)
     {
@@ -1039,7 +1043,13 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
         mbar_wait(ds_ready, (uint32_t)(j & 1));
         tc_fence_after();
         if (elect_one()) {
-          mma_pv(tdV, smem_u32(sPT), smem_u32(sdO + st * q_tile), BQ * 128, BQ, idesc_o, j > 0 ? 1u : 0u);
+          if constexpr (PT) {
+            for (int ks = 0; ks < BQ / 16; ++ks)   // A = Pᵀ[:, 16 ks .. 16 ks + 16) = 8 TMEM columns
+              umma_bf16_ts(tdV, tPT + (uint32_t)(ks * 8), umma_desc(smem_u32(sdO + st * q_tile) + ks * 2048, BQ * 128, 1024),
+                           idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
+          } else {
+            mma_pv(tdV, smem_u32(sPT), smem_u32(sdO + st * q_tile), BQ * 128, BQ, idesc_o, j > 0 ? 1u : 0u);
+          }
           mma_pv(tdK, smem_u32(sdST), smem_u32(sQ + st * q_tile), BQ * 128, BQ, idesc_o, j > 0 ? 1u : 0u);
         }
         if (j > 0) {
@@ -1164,14 +1174,20 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
 #pragma unroll
           for (int e = 0; e < 8; ++e) wp[e] = wd[e] = 0u;
         }
-        uint8_t* pp = sPT + (c >> 6) * 16384 + rowoff;
         uint8_t* pd = sdST + (c >> 6) * 16384 + rowoff;
         const uint32_t cb = (uint32_t)((c & 63) >> 3);
-        *reinterpret_cast<uint4*>(pp + ((cb ^ r7) << 4)) = make_uint4(wp[0], wp[1], wp[2], wp[3]);
-        *reinterpret_cast<uint4*>(pp + (((cb + 1) ^ r7) << 4)) = make_uint4(wp[4], wp[5], wp[6], wp[7]);
+        if constexpr (PT) {
+          __syncwarp();
+          tmem_st8(tPT + lane_base + (uint32_t)(c >> 1), wp);   // 16 bf16 of this key row -> 8 columns
+        } else {
+          uint8_t* pp = sPT + (c >> 6) * 16384 + rowoff;
+          *reinterpret_cast<uint4*>(pp + ((cb ^ r7) << 4)) = make_uint4(wp[0], wp[1], wp[2], wp[3]);
+          *reinterpret_cast<uint4*>(pp + (((cb + 1) ^ r7) << 4)) = make_uint4(wp[4], wp[5], wp[6], wp[7]);
+        }
         *reinterpret_cast<uint4*>(pd + ((cb ^ r7) << 4)) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
         *reinterpret_cast<uint4*>(pd + (((cb + 1) ^ r7) << 4)) = make_uint4(wd[4], wd[5], wd[6], wd[7]);
       }
+      if constexpr (PT) tmem_st_wait();
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(ds_ready);
@@ -1742,9 +1758,11 @@ extern "C" int e4t_attn_bwd_fused(const void* Q, const void* K, const void* V, c
   E4T_CUDA(cudaMemsetAsync(dQacc, 0, (size_t)nacc * sizeof(float), st));
   static bool attr = false;
   if (!attr) {
-    E4T_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    E4T_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    E4T_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    E4T_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel<2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    E4T_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel<4, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    E4T_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel<4, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    E4T_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel<4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    E4T_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel<4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     E4T_CUDA(cudaFuncSetAttribute(attn_bwd_fused_pp_kernel<4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     E4T_CUDA(cudaFuncSetAttribute(attn_bwd_fused_pp_kernel<2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     E4T_CUDA(cudaFuncSetAttribute(attn_bwd_fused_pp_kernel<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -1776,6 +1794,9 @@ extern "C" int e4t_attn_bwd_fused(const void* Q, const void* K, const void* V, c
   // opt-in: dQ through a TMA reduce-add (needs 2 x 128 x dh fp32 of extra shared memory: dh <= 64 only)
   const char* dqe = getenv("E4T_ATTN_DQ_TMA");
   const bool dq_tma = !pp && a.DC == 1 && dqe && atoi(dqe) != 0 && smem + (size_t)2 * 128 * dh * 4 <= 227 * 1024;
+  // opt-in: Pᵀ through TMEM (256 + 3*dpad + 64 columns must fit 512: dpad <= 64)
+  const char* pte = getenv("E4T_ATTN_PT_TMEM");
+  const bool pt_tmem = !pp && pte && atoi(pte) != 0 && 256 + 3 * dpad + 64 <= 512;
   CUtensorMap mDQ;
   memset(&mDQ, 0, sizeof(mDQ));
   if (dq_tma) {
@@ -1791,11 +1812,17 @@ extern "C" int e4t_attn_bwd_fused(const void* Q, const void* K, const void* V, c
     else if (pp == 2) attn_bwd_fused_pp_kernel<2, 16><<<grid, 128 + 128 * 2, smem_pp, st>>>(mQ, mK, mV, mdO, a, dQacc);
     else if (pp == 3) attn_bwd_fused_pp_kernel<2, 8><<<grid, 128 + 128 * 2, smem_pp, st>>>(mQ, mK, mV, mdO, a, dQacc);
     else attn_bwd_fused_pp_kernel<4, 16><<<grid, 128 + 128 * 4, smem_pp, st>>>(mQ, mK, mV, mdO, a, dQacc);
-  } else if (dq_tma) {
-    attn_bwd_fused_kernel<4, true><<<dim3(cdiv(M, 128), H, B), 128 + 128 * 4, smem + 2 * 128 * dh * 4, st>>>(
+  } else if (dq_tma && pt_tmem) {
+    attn_bwd_fused_kernel<4, true, true><<<dim3(cdiv(M, 128), H, B), 128 + 128 * 4, smem + 2 * 128 * dh * 4, st>>>(
         mQ, mK, mV, mdO, mDQ, a, dQacc);
-  } else if (attn_cg(1) == 4) attn_bwd_fused_kernel<4, false><<<dim3(cdiv(M, 128), H, B), 128 + 128 * 4, smem, st>>>(mQ, mK, mV, mdO, mDQ, a, dQacc);
-  else attn_bwd_fused_kernel<2, false><<<dim3(cdiv(M, 128), H, B), 128 + 128 * 2, smem, st>>>(mQ, mK, mV, mdO, mDQ, a, dQacc);
+  } else if (dq_tma) {
+    attn_bwd_fused_kernel<4, true, false><<<dim3(cdiv(M, 128), H, B), 128 + 128 * 4, smem + 2 * 128 * dh * 4, st>>>(
+        mQ, mK, mV, mdO, mDQ, a, dQacc);
+  } else if (pt_tmem) {
+    attn_bwd_fused_kernel<4, false, true><<<dim3(cdiv(M, 128), H, B), 128 + 128 * 4, smem, st>>>(mQ, mK, mV, mdO, mDQ, a,
+                                                                                                  dQacc);
+  } else if (attn_cg(1) == 4) attn_bwd_fused_kernel<4, false, false><<<dim3(cdiv(M, 128), H, B), 128 + 128 * 4, smem, st>>>(mQ, mK, mV, mdO, mDQ, a, dQacc);
+  else attn_bwd_fused_kernel<2, false, false><<<dim3(cdiv(M, 128), H, B), 128 + 128 * 2, smem, st>>>(mQ, mK, mV, mdO, mDQ, a, dQacc);
   E4T_COUNT_LAUNCH();
   E4T_LAUNCH_CHECK();
   const long long total_vec = (long long)B * N * (H * dh / 8);

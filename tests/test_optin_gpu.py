@@ -12,7 +12,8 @@ import torch
 pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(os.environ.get("E4T_TEST_OPTIN") != "1", reason="opt-in variants: set E4T_TEST_OPTIN=1")]
 
-SWITCHES = ("E4T_ATTN_PP", "E4T_ATTN_DQ_TMA", "E4T_ATTN_DELTA2", "E4T_GEMM_EPI_PLAIN", "E4T_ATTN_CG")
+SWITCHES = ("E4T_ATTN_PP", "E4T_ATTN_DQ_TMA", "E4T_ATTN_DELTA2", "E4T_ATTN_PT_TMEM", "E4T_GEMM_EPI_PLAIN",
+            "E4T_ATTN_CG")
 
 
 @pytest.fixture(autouse=True)
@@ -35,6 +36,7 @@ def _rel(a, b):
 
 @pytest.mark.parametrize("env", [{"E4T_ATTN_PP": "1"}, {"E4T_ATTN_PP": "2"}, {"E4T_ATTN_PP": "3"}, {"E4T_ATTN_PP": "4"},
                                  {"E4T_ATTN_DQ_TMA": "1"}, {"E4T_ATTN_DELTA2": "1"},
+                                 {"E4T_ATTN_PT_TMEM": "1"}, {"E4T_ATTN_PT_TMEM": "1", "E4T_ATTN_DQ_TMA": "1"},
                                  {"E4T_ATTN_DQ_TMA": "1", "E4T_ATTN_DELTA2": "1"}])
 @pytest.mark.parametrize("B,H,N,M,dh", [(2, 8, 256, 256, 40), (2, 8, 1024, 77, 40), (2, 4, 256, 256, 16),
                                         (1, 8, 300, 200, 40), (1, 4, 384, 128, 64), (1, 8, 1024, 1024, 80),

@@ -203,10 +203,12 @@ def sweep_attn(B=16):
     fwd_variants = {"default": None, "cg4_occ1": "4,4,4,0", "cg2_occ1": "2,4,4,0", "cg2_occ2": "2,4,4,1"}
     bwd_variants = {"default": {}, "pp1": {"E4T_ATTN_PP": 1}, "pp2": {"E4T_ATTN_PP": 2}, "pp4": {"E4T_ATTN_PP": 4},
                     "dq_tma": {"E4T_ATTN_DQ_TMA": 1}, "fused_cg2": {"E4T_ATTN_CG": "4,2,4,1"},
-                    "delta2": {"E4T_ATTN_DELTA2": 1}, "delta2+dq_tma": {"E4T_ATTN_DELTA2": 1, "E4T_ATTN_DQ_TMA": 1}}
+                    "delta2": {"E4T_ATTN_DELTA2": 1}, "pt_tmem": {"E4T_ATTN_PT_TMEM": 1},
+                    "pt+dq": {"E4T_ATTN_PT_TMEM": 1, "E4T_ATTN_DQ_TMA": 1},
+                    "pt+dq+delta2": {"E4T_ATTN_PT_TMEM": 1, "E4T_ATTN_DQ_TMA": 1, "E4T_ATTN_DELTA2": 1}}
     for (N, M, C) in shapes:
         q, k, v, do = bf(B, N, C, scale=0.5), bf(B, M, C, scale=0.5), bf(B, M, C, scale=0.5), bf(B, N, C)
-        set_env(E4T_ATTN_CG=None, E4T_ATTN_PP=None, E4T_ATTN_DQ_TMA=None, E4T_ATTN_DELTA2=None)
+        set_env(E4T_ATTN_CG=None, E4T_ATTN_PP=None, E4T_ATTN_DQ_TMA=None, E4T_ATTN_DELTA2=None, E4T_ATTN_PT_TMEM=None)
         o0, lse0 = ops.attn_fwd(q, k, v, 8)
         g0 = ops.attn_bwd(q, k, v, o0, do, lse0, 8)
         torch.cuda.synchronize()
@@ -221,7 +223,7 @@ def sweep_attn(B=16):
                 row["fwd"][name] = {"error": str(ex)[:120]}
         set_env(E4T_ATTN_CG=None)
         for name, env in bwd_variants.items():
-            set_env(E4T_ATTN_CG=None, E4T_ATTN_PP=None, E4T_ATTN_DQ_TMA=None, E4T_ATTN_DELTA2=None)
+            set_env(E4T_ATTN_CG=None, E4T_ATTN_PP=None, E4T_ATTN_DQ_TMA=None, E4T_ATTN_DELTA2=None, E4T_ATTN_PT_TMEM=None)
             set_env(**env)
             try:
                 g = ops.attn_bwd(q, k, v, o0, do, lse0, 8)
@@ -230,7 +232,7 @@ def sweep_attn(B=16):
                 row["bwd"][name] = {"err": max(errs), "ms": timeit(lambda: ops.attn_bwd(q, k, v, o0, do, lse0, 8))}
             except Exception as ex:
                 row["bwd"][name] = {"error": str(ex)[:120]}
-        set_env(E4T_ATTN_CG=None, E4T_ATTN_PP=None, E4T_ATTN_DQ_TMA=None, E4T_ATTN_DELTA2=None)
+        set_env(E4T_ATTN_CG=None, E4T_ATTN_PP=None, E4T_ATTN_DQ_TMA=None, E4T_ATTN_DELTA2=None, E4T_ATTN_PT_TMEM=None)
         print(f"[attn] N={N} M={M} dh={C//8}: fwd " +
               " ".join(f"{n}={d.get('ms', float('nan')):.3f}" for n, d in row["fwd"].items()) + " | bwd " +
               " ".join(f"{n}={d.get('ms', float('nan')):.3f}(e{d.get('err', 0):.0e})" for n, d in row["bwd"].items()))
