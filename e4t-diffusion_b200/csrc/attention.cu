@@ -64,6 +64,15 @@ __device__ __forceinline__ void mma_pv(uint32_t d_tmem, uint32_t sP, uint32_t sV
   }
 }
 
+__device__ __forceinline__ void mma_pv_ts(uint32_t d_tmem, uint32_t tP, uint32_t sV, uint32_t v_chunk, int kdim,
+                                          uint32_t idesc, uint32_t acc) {
+  // as mma_pv with the A operand P[128][kdim] in TMEM: K-step ks = 8 columns (two bf16 per column)
+  for (int ks = 0; ks < kdim / 16; ++ks) {
+    umma_bf16_ts(d_tmem, tP + (uint32_t)(ks * 8), umma_desc(sV + ks * 2048, v_chunk, 1024), idesc, acc);
+    acc = 1;
+  }
+}
+
 __device__ __forceinline__ float max32(const uint32_t* v, float mx) {
 #pragma unroll
   for (int e = 0; e < 32; e += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(v[e]), __uint_as_float(v[e + 1])));
@@ -85,7 +94,10 @@ __device__ __forceinline__ void sts_row32(uint8_t* tile, uint32_t rowoff, uint32
 //   SM sub-partition has CG resident softmax warps to overlap MUFU / FMA / TMEM latencies.  Row maxima are exchanged
 //   through shared memory (double buffered), row sums are combined once at the end.
 // =============================================================================================
-template <int CG, int OCC>
+// PT (opt-in, E4T_ATTN_FWD_PT=1): P is written to TMEM (tcgen05.st, two bf16 per column) and O += P·V reads its A operand
+// from there (tcgen05.mma [d], [a], bdesc): no P round trip through shared memory, and the N = dpad MMAs stop being bound
+// by the 4 KiB A-tile read per instruction.
+template <int CG, int OCC, bool PT>
 __global__ void __launch_bounds__(128 + 128 * CG, OCC)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                 const __grid_constant__ CUtensorMap mapV, const AttnArgs a) {
@@ -138,6 +150,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t tS0 = tmem, tO = tmem + (uint32_t)a.sbuf * 128u;
+  const uint32_t tP0 = tO + (uint32_t)a.dpad;   // PT: pbuf x 64 columns
 
   // Producer and MMA warps run their control flow with all 32 lanes and issue under elect_one(): ptxas then knows a
   // single thread is active and emits the TMA / tcgen05 instructions without a per-lane retry loop.
@@ -199,8 +212,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
             mbar_wait(&v_full[st], (uint32_t)((j / a.kst) & 1));
             tc_fence_after();
             if (elect_one()) {
-              mma_pv(tO, smem_u32(sP0 + (j & (a.pbuf - 1)) * p_bytes), smem_u32(sV + st * kv_tile), a.BKV * 128,
-                     a.BKV, idesc_o, j > 0 ? 1u : 0u);
+              if constexpr (PT)
+                mma_pv_ts(tO, tP0 + (uint32_t)(j & (a.pbuf - 1)) * 64u, smem_u32(sV + st * kv_tile), a.BKV * 128, a.BKV,
+                          idesc_o, j > 0 ? 1u : 0u);
+              else
+                mma_pv(tO, smem_u32(sP0 + (j & (a.pbuf - 1)) * p_bytes), smem_u32(sV + st * kv_tile), a.BKV * 128,
+                       a.BKV, idesc_o, j > 0 ? 1u : 0u);
               umma_commit(&v_empty[st]);
               umma_commit(&p_free[j & (a.pbuf - 1)]);
               umma_commit(o_done);
@@ -222,6 +239,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
     for (int j = 0; j < a.nblk; ++j) {
       const uint32_t tS = tS0 + (uint32_t)(j & (a.sbuf - 1)) * 128u + lane_base;
       uint8_t* sP = sP0 + (j & (a.pbuf - 1)) * p_bytes;
+      const uint32_t tP = tP0 + (uint32_t)(j & (a.pbuf - 1)) * 64u + lane_base;
       mbar_wait(&s_full[j & (a.sbuf - 1)], (uint32_t)((j / a.sbuf) & 1));
       tc_fence_after();
       if (a.BKV == 128 && (j + 1) * 128 <= a.M) {
@@ -264,7 +282,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
             rs1 += p1;
             w[e] = pack_bf16(p0, p1);
           }
-          sts_row32(sP, rowoff, r7, col0, w);
+          if constexpr (PT) {
+            __syncwarp();
+            tmem_st16(tP + (uint32_t)(col0 >> 1), w);
+          } else {
+            sts_row32(sP, rowoff, r7, col0, w);
+          }
         }
         l = l * alpha + (rs0 + rs1);
         m = m_new;
@@ -281,6 +304,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
           }
           tmem_st_wait();
         }
+        if constexpr (PT) tmem_st_wait();
         fence_proxy_async_smem();
         tc_fence_before();
         mbar_arrive(p_ready);
@@ -363,10 +387,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
             rs += p0 + p1;
             w[e] = pack_bf16(p0, p1);
           }
-          uint8_t* pc = sP + (ci >> 2) * 16384;
-          const uint32_t c16 = (uint32_t)((ci & 3) * 2);
-          *reinterpret_cast<uint4*>(pc + sw128_off((uint32_t)row, c16)) = make_uint4(w[0], w[1], w[2], w[3]);
-          *reinterpret_cast<uint4*>(pc + sw128_off((uint32_t)row, c16 + 1)) = make_uint4(w[4], w[5], w[6], w[7]);
+          if constexpr (PT) {
+            __syncwarp();
+            tmem_st8(tP + (uint32_t)(ci * 8), w);
+          } else {
+            uint8_t* pc = sP + (ci >> 2) * 16384;
+            const uint32_t c16 = (uint32_t)((ci & 3) * 2);
+            *reinterpret_cast<uint4*>(pc + sw128_off((uint32_t)row, c16)) = make_uint4(w[0], w[1], w[2], w[3]);
+            *reinterpret_cast<uint4*>(pc + sw128_off((uint32_t)row, c16 + 1)) = make_uint4(w[4], w[5], w[6], w[7]);
+          }
         }
       }
       l = l * alpha + rs;
@@ -385,6 +414,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
         }
         tmem_st_wait();
       }
+      if constexpr (PT) tmem_st_wait();
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(p_ready);
@@ -1642,15 +1672,26 @@ extern "C" int e4t_attn_fwd(const void* Q, const void* K, const void* V, void* O
   const size_t smem = smem_base + a.pbuf * p_bytes;
   static bool attr = false;
   if (!attr) {
-    E4T_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    E4T_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    E4T_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+    E4T_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<2, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    E4T_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<4, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    E4T_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<2, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
+    E4T_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<2, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    E4T_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<4, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    E4T_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<2, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024));
     attr = true;
   }
   E4T_CHECK(smem <= (occ2 ? 113 : 227) * 1024, "e4t_attn_fwd: smem budget exceeded (%zu)", smem);
-  if (occ2) attn_fwd_kernel<2, 2><<<dim3(cdiv(N, 128), H, B), 128 + 128 * 2, smem, st>>>(mQ, mK, mV, a);
-  else if (cg == 4) attn_fwd_kernel<4, 1><<<dim3(cdiv(N, 128), H, B), 128 + 128 * 4, smem, st>>>(mQ, mK, mV, a);
-  else attn_fwd_kernel<2, 1><<<dim3(cdiv(N, 128), H, B), 128 + 128 * 2, smem, st>>>(mQ, mK, mV, a);
+  // opt-in: P through TMEM (needs sbuf*128 + dpad + pbuf*64 columns)
+  const char* pte = getenv("E4T_ATTN_FWD_PT");
+  const bool pt = pte && atoi(pte) != 0 && a.sbuf * 128 + a.dpad + a.pbuf * 64 <= a.tmem_cols;
+  const dim3 grid(cdiv(N, 128), H, B);
+  if (pt) {
+    if (occ2) attn_fwd_kernel<2, 2, true><<<grid, 128 + 128 * 2, smem, st>>>(mQ, mK, mV, a);
+    else if (cg == 4) attn_fwd_kernel<4, 1, true><<<grid, 128 + 128 * 4, smem, st>>>(mQ, mK, mV, a);
+    else attn_fwd_kernel<2, 1, true><<<grid, 128 + 128 * 2, smem, st>>>(mQ, mK, mV, a);
+  } else if (occ2) attn_fwd_kernel<2, 2, false><<<grid, 128 + 128 * 2, smem, st>>>(mQ, mK, mV, a);
+  else if (cg == 4) attn_fwd_kernel<4, 1, false><<<grid, 128 + 128 * 4, smem, st>>>(mQ, mK, mV, a);
+  else attn_fwd_kernel<2, 1, false><<<grid, 128 + 128 * 2, smem, st>>>(mQ, mK, mV, a);
   E4T_COUNT_LAUNCH();
   E4T_LAUNCH_CHECK();
   return 0;

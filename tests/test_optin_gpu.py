@@ -12,7 +12,7 @@ import torch
 pytestmark = [pytest.mark.gpu,
               pytest.mark.skipif(os.environ.get("E4T_TEST_OPTIN") != "1", reason="opt-in variants: set E4T_TEST_OPTIN=1")]
 
-SWITCHES = ("E4T_ATTN_PP", "E4T_ATTN_DQ_TMA", "E4T_ATTN_DELTA2", "E4T_ATTN_PT_TMEM", "E4T_GEMM_EPI_PLAIN",
+SWITCHES = ("E4T_ATTN_PP", "E4T_ATTN_DQ_TMA", "E4T_ATTN_DELTA2", "E4T_ATTN_PT_TMEM", "E4T_ATTN_FWD_PT", "E4T_GEMM_EPI_PLAIN",
             "E4T_ATTN_CG")
 
 
@@ -54,6 +54,24 @@ def test_attention_backward_variants_match_default(env, B, H, N, M, dh):
     torch.cuda.synchronize()
     for name, a, b in zip(("dq", "dk", "dv"), got, ref):
         assert _rel(a, b) < 2e-3, (name, env, _rel(a, b))     # same math, different accumulation order for dQ
+
+
+@pytest.mark.parametrize("cg", [None, "4,4,4,0", "2,4,4,0"])
+@pytest.mark.parametrize("B,H,N,M,dh", [(2, 8, 256, 256, 40), (2, 8, 1024, 77, 40), (1, 8, 300, 200, 80),
+                                        (2, 8, 256, 256, 160), (2, 4, 64, 77, 32), (1, 8, 4096, 4096, 40)])
+def test_attention_forward_p_in_tmem_matches_default(cg, B, H, N, M, dh):
+    from e4t_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(N + M + dh)
+    C = H * dh
+    q, k, v = _mk((B, N, C), g), _mk((B, M, C), g), _mk((B, M, C), g)
+    if cg:
+        os.environ["E4T_ATTN_CG"] = cg
+    o0, lse0 = ops.attn_fwd(q, k, v, H)
+    os.environ["E4T_ATTN_FWD_PT"] = "1"
+    o1, lse1 = ops.attn_fwd(q, k, v, H)
+    torch.cuda.synchronize()
+    assert torch.equal(lse0, lse1)
+    assert _rel(o1, o0) < 1e-3, _rel(o1, o0)      # same P values, same MMAs: expected bit-identical
 
 
 @pytest.mark.parametrize("M,N,K,b_mn", [(4096, 960, 320, False), (8192, 320, 320, False), (4096, 2560, 320, False),

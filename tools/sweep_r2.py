@@ -200,7 +200,8 @@ def set_env(**kw):
 def sweep_attn(B=16):
     out = []
     shapes = [(4096, 4096, 320), (1024, 1024, 640), (256, 256, 1280), (4096, 77, 320), (1024, 77, 640)]
-    fwd_variants = {"default": None, "cg4_occ1": "4,4,4,0", "cg2_occ1": "2,4,4,0", "cg2_occ2": "2,4,4,1"}
+    fwd_variants = {"default": {}, "cg4_occ1": {"E4T_ATTN_CG": "4,4,4,0"}, "cg2_occ1": {"E4T_ATTN_CG": "2,4,4,0"},
+                    "pt": {"E4T_ATTN_FWD_PT": 1}, "cg4_occ1+pt": {"E4T_ATTN_CG": "4,4,4,0", "E4T_ATTN_FWD_PT": 1}}
     bwd_variants = {"default": {}, "pp1": {"E4T_ATTN_PP": 1}, "pp2": {"E4T_ATTN_PP": 2}, "pp4": {"E4T_ATTN_PP": 4},
                     "dq_tma": {"E4T_ATTN_DQ_TMA": 1}, "fused_cg2": {"E4T_ATTN_CG": "4,2,4,1"},
                     "delta2": {"E4T_ATTN_DELTA2": 1}, "pt_tmem": {"E4T_ATTN_PT_TMEM": 1},
@@ -213,15 +214,16 @@ def sweep_attn(B=16):
         g0 = ops.attn_bwd(q, k, v, o0, do, lse0, 8)
         torch.cuda.synchronize()
         row = {"N": N, "M": M, "dh": C // 8, "fwd": {}, "bwd": {}}
-        for name, cg in fwd_variants.items():
-            set_env(E4T_ATTN_CG=cg)
+        for name, env in fwd_variants.items():
+            set_env(E4T_ATTN_CG=None, E4T_ATTN_FWD_PT=None)
+            set_env(**env)
             try:
                 o, lse = ops.attn_fwd(q, k, v, 8)
                 torch.cuda.synchronize()
                 row["fwd"][name] = {"err": rel(o, o0), "ms": timeit(lambda: ops.attn_fwd(q, k, v, 8))}
             except Exception as ex:
                 row["fwd"][name] = {"error": str(ex)[:120]}
-        set_env(E4T_ATTN_CG=None)
+        set_env(E4T_ATTN_CG=None, E4T_ATTN_FWD_PT=None)
         for name, env in bwd_variants.items():
             set_env(E4T_ATTN_CG=None, E4T_ATTN_PP=None, E4T_ATTN_DQ_TMA=None, E4T_ATTN_DELTA2=None, E4T_ATTN_PT_TMEM=None)
             set_env(**env)
