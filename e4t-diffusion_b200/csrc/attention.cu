@@ -18,74 +18,7 @@
 #include "common.cuh"
 #include <stdlib.h>
 
-static constexpr float kLog2e = 1.4426950408889634f;
-
-struct AttnArgs {
-  int B, H, N, M, dh;
-  int DC;        // 64-wide chunks of dh
-  int dpad;      // dh rounded up to 16 (MMA N of the output GEMMs)
-  int BKV;       // key/value block (fwd, dQ) or query block (dKV), multiple of 16
-  int nblk;      // number of blocks looped over
-  int kst;       // ring stages
-  int sbuf;      // fwd: S accumulator buffers in TMEM (2 = software pipelined, 1 = rely on 2 CTAs/SM)
-  int pbuf;      // fwd: P buffers in smem (2 = softmax never waits for the previous P·V to retire)
-  int tmem_cols; // TMEM columns to allocate (256 lets two CTAs share an SM)
-  float scale;   // dh^-0.5
-  // pointers / strides (elements)
-  bf16* O;  long long ldo, o_bs;
-  float* LSE;    // [B][H][N]
-  const float* Dv;  // [B][H][N] rowsum(dO∘O)
-  bf16* dQ; long long lddq, dq_bs;
-  bf16* dK; long long lddk, dk_bs;
-  bf16* dV; long long lddv, dv_bs;
-};
-
-__device__ __forceinline__ void mma_kmajor(uint32_t d_tmem, uint32_t sA, uint32_t a_chunk, uint32_t sB,
-                                           uint32_t b_chunk, int dh, int DC, uint32_t idesc) {
-  // D = A[128][dh] · B[N][dh]ᵀ, both K-major, dh split in 64-wide chunks
-  uint32_t acc = 0;
-  for (int c = 0; c < DC; ++c) {
-    const int rem = dh - 64 * c;
-    const int ks = rem >= 64 ? 4 : (rem + 15) / 16;
-    for (int k = 0; k < ks; ++k) {
-      umma_bf16(d_tmem, umma_desc(sA + c * a_chunk + k * 32, 16, 1024), umma_desc(sB + c * b_chunk + k * 32, 16, 1024),
-                idesc, acc);
-      acc = 1;
-    }
-  }
-}
-__device__ __forceinline__ void mma_pv(uint32_t d_tmem, uint32_t sP, uint32_t sV, uint32_t v_chunk, int kdim,
-                                       uint32_t idesc, uint32_t acc) {
-  // D[128][dpad] (+)= P[128][kdim] (K-major, 64-col chunks of 16 KiB) · V[kdim][dpad] (MN-major, 64-wide d chunks)
-  for (int ks = 0; ks < kdim / 16; ++ks) {
-    umma_bf16(d_tmem, umma_desc(sP + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
-              umma_desc(sV + ks * 2048, v_chunk, 1024), idesc, acc);
-    acc = 1;
-  }
-}
-
-__device__ __forceinline__ void mma_pv_ts(uint32_t d_tmem, uint32_t tP, uint32_t sV, uint32_t v_chunk, int kdim,
-                                          uint32_t idesc, uint32_t acc) {
-  // as mma_pv with the A operand P[128][kdim] in TMEM: K-step ks = 8 columns (two bf16 per column)
-  for (int ks = 0; ks < kdim / 16; ++ks) {
-    umma_bf16_ts(d_tmem, tP + (uint32_t)(ks * 8), umma_desc(sV + ks * 2048, v_chunk, 1024), idesc, acc);
-    acc = 1;
-  }
-}
-
-__device__ __forceinline__ float max32(const uint32_t* v, float mx) {
-#pragma unroll
-  for (int e = 0; e < 32; e += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(v[e]), __uint_as_float(v[e + 1])));
-  return mx;
-}
-// store 32 bf16 (packed in w[16]) of row `rowoff/128` at columns [col0, col0+32) of a K-major SWIZZLE_128B tile set
-__device__ __forceinline__ void sts_row32(uint8_t* tile, uint32_t rowoff, uint32_t r7, int col0, const uint32_t* w) {
-  uint8_t* pc = tile + (col0 >> 6) * 16384 + rowoff;
-  const uint32_t cb = (uint32_t)((col0 & 63) >> 3);
-#pragma unroll
-  for (int q = 0; q < 4; ++q)
-    *reinterpret_cast<uint4*>(pc + (((cb + q) ^ r7) << 4)) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
-}
+#include "attn_common.cuh"
 
 // =============================================================================================
 // Forward
@@ -1262,322 +1195,6 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
   }
 }
 
-// =============================================================================================
-// Fused backward, half-tile ping-pong variant (dh <= 64 so that two Q/dO stages fit).  Same maths and TMEM map as
-// attn_bwd_fused_kernel; the 128-query block is split in two 64-query halves, each with its own barriers:
-//   tensor core: [Sᵀ,dPᵀ](j+1, half 0) and the half-0 k-steps of dV/dK(j) run while the threads work on half 1 of block
-//                j; dV/dK(j, half 1), dQ(j) and [Sᵀ,dPᵀ](j+1, half 1) run while they work on half 0 of block j+1
-//   threads    : do not wait for the tensor core in steady state; TMEM loads are software pipelined (the next G-column
-//                granule is in flight while the current one is exponentiated); LSE/D of a block are staged per warp
-//                (no CTA-wide barrier inside the loop) and fetched one block ahead
-// dSᵀ is double buffered in smem (dQ(j) still reads it when the threads start block j+1); Pᵀ is not: the readers of
-// half h retire before Sᵀ(j+1, h) is committed, and the threads only write half h after that commit.
-// =============================================================================================
-template <int G>
-__device__ __forceinline__ void tmem_ldG(uint32_t taddr, uint32_t* r) {
-  if constexpr (G == 16) tmem_ld16(taddr, r);
-  else tmem_ld8(taddr, r);
-}
-__device__ __forceinline__ void mma_pv_range(uint32_t d_tmem, uint32_t sP, uint32_t sV, uint32_t v_chunk, int ks0,
-                                             int ks1, uint32_t idesc, uint32_t acc) {
-  for (int ks = ks0; ks < ks1; ++ks) {
-    umma_bf16(d_tmem, umma_desc(sP + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
-              umma_desc(sV + ks * 2048, v_chunk, 1024), idesc, acc);
-    acc = 1;
-  }
-}
-
-template <int CG, int G>
-__global__ void __launch_bounds__(128 + 128 * CG, 1)
-attn_bwd_fused_pp_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
-                         const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapdO,
-                         const AttnArgs a, float* __restrict__ dQacc) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  constexpr int BQ = 128;
-  constexpr int W = 64 / CG;     // query columns one warp owns in each half
-  constexpr int GH = W / G;      // granules per half
-  constexpr int NG = 2 * GH;     // granules per block
-  constexpr int NL = 2 * W / 32; // LSE/D values each lane stages per block
-  static_assert(GH >= 1 && NL >= 1, "granule / column-group combination");
-  uint8_t* sK = smem;                 // 16 KiB
-  uint8_t* sV = sK + 16384;           // 16 KiB
-  uint8_t* sQ = sV + 16384;           // 2 stages x 16 KiB
-  uint8_t* sdO = sQ + 32768;          // 2 stages x 16 KiB
-  uint8_t* sPT = sdO + 32768;         // 2 halves x 16 KiB
-  uint8_t* sdST = sPT + 32768;        // 2 buffers x 2 halves x 16 KiB
-  float* sLD = reinterpret_cast<float*>(sdST + 65536);  // [4*CG warps][2 arrays][2W]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sLD + 4 * CG * 4 * W);
-  uint64_t* kv_full = bars;
-  uint64_t* q_full = bars + 1;    // [2]
-  uint64_t* q_empty = bars + 3;   // [2]
-  uint64_t* sp_full = bars + 5;   // [2] per half
-  uint64_t* ds_ready = bars + 7;  // [2] per half
-  uint64_t* acc_done = bars + 9;
-  uint64_t* dq_full = bars + 10;
-  uint64_t* dq_empty = bars + 11;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int k0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
-  if (warp == 1 && lane == 0) {
-    mbar_init(kv_full, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&q_full[i], 1);
-      mbar_init(&q_empty[i], 1);
-      mbar_init(&sp_full[i], 1);
-      mbar_init(&ds_ready[i], 128 * CG);
-    }
-    mbar_init(acc_done, 1);
-    mbar_init(dq_full, 1);
-    mbar_init(dq_empty, 128 * CG);
-    fence_mbar_init();
-  }
-  if (warp == 2) tmem_alloc(tmem_slot, 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  const uint32_t tST = tmem, tdPT = tmem + 128, tdV = tmem + 256, tdK = tdV + (uint32_t)a.dpad,
-                 tdQ = tdK + (uint32_t)a.dpad;
-
-  if (warp == 0) {   // whole warp runs the control flow, one elected lane issues (see attn_fwd_kernel)
-    {
-      if (elect_one()) {
-        mbar_expect_tx(kv_full, 32768u);
-        tma_load_4d(sK, &mapK, kv_full, 0, h, k0, b);
-        tma_load_4d(sV, &mapV, kv_full, 0, h, k0, b);
-      }
-      for (int j = 0; j < a.nblk; ++j) {
-        const int st = j & 1;
-        mbar_wait(&q_empty[st], (uint32_t)(((j >> 1) & 1) ^ 1));
-        if (elect_one()) {
-          mbar_expect_tx(&q_full[st], 32768u);
-          tma_load_4d(sQ + st * 16384, &mapQ, &q_full[st], 0, h, j * BQ, b);
-          tma_load_4d(sdO + st * 16384, &mapdO, &q_full[st], 0, h, j * BQ, b);
-        }
-      }
-    }
-  } else if (warp == 1) {
-    {
-      const uint32_t idesc_s = umma_idesc_bf16(64u, false, false);
-      const uint32_t idesc_o = umma_idesc_bf16((uint32_t)a.dpad, false, true);
-      const uint32_t idesc_q = umma_idesc_bf16((uint32_t)a.dpad, true, true);
-      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aQ = smem_u32(sQ), adO = smem_u32(sdO),
-                     aPT = smem_u32(sPT), adST = smem_u32(sdST);
-      // Sᵀ / dPᵀ columns [64*hf, 64*hf+64) of the block staged in `st`: B operand = query rows 64*hf.. of the tile
-      auto issue_sp = [&](int st, int hf) {
-        mma_kmajor(tST + (uint32_t)(64 * hf), aK, 16384, aQ + st * 16384 + hf * 8192, 16384, a.dh, 1, idesc_s);
-        mma_kmajor(tdPT + (uint32_t)(64 * hf), aV, 16384, adO + st * 16384 + hf * 8192, 16384, a.dh, 1, idesc_s);
-      };
-      mbar_wait(kv_full, 0);
-      mbar_wait(&q_full[0], 0);
-      tc_fence_after();
-      if (elect_one()) {
-        issue_sp(0, 0);
-        umma_commit(&sp_full[0]);
-        issue_sp(0, 1);
-        umma_commit(&sp_full[1]);
-      }
-      for (int j = 0; j < a.nblk; ++j) {
-        const int st = j & 1;
-        const uint32_t ds = adST + (uint32_t)(j & 1) * 32768u;
-        const bool more = j + 1 < a.nblk;
-        mbar_wait(&ds_ready[0], (uint32_t)(j & 1));
-        tc_fence_after();
-        if (elect_one()) {
-          mma_pv_range(tdV, aPT, adO + st * 16384, 16384, 0, 4, idesc_o, j > 0 ? 1u : 0u);
-          mma_pv_range(tdK, ds, aQ + st * 16384, 16384, 0, 4, idesc_o, j > 0 ? 1u : 0u);
-        }
-        if (more) {
-          mbar_wait(&q_full[st ^ 1], (uint32_t)(((j + 1) >> 1) & 1));
-          tc_fence_after();
-          if (elect_one()) {
-            issue_sp(st ^ 1, 0);
-            umma_commit(&sp_full[0]);
-          }
-        }
-        mbar_wait(&ds_ready[1], (uint32_t)(j & 1));
-        tc_fence_after();
-        if (elect_one()) {
-          mma_pv_range(tdV, aPT, adO + st * 16384, 16384, 4, 8, idesc_o, 1u);
-          mma_pv_range(tdK, ds, aQ + st * 16384, 16384, 4, 8, idesc_o, 1u);
-          if (more) {   // before dQ(j): the threads want half 1 of block j+1 one granule after they start that block
-            issue_sp(st ^ 1, 1);
-            umma_commit(&sp_full[1]);
-          }
-        }
-        if (j > 0) {
-          mbar_wait(dq_empty, (uint32_t)((j - 1) & 1));  // threads have drained dQ_blk of block j-1
-          tc_fence_after();
-        }
-        if (elect_one()) {
-          mma_ds_k(tdQ, ds, aK, 16384, idesc_q);
-          umma_commit(&q_empty[st]);
-          umma_commit(dq_full);
-          umma_commit(acc_done);
-        }
-      }
-    }
-  } else if (warp >= 4) {
-    const int sw = warp - 4;
-    const int ew = sw & 3;
-    const int cg = sw >> 2;
-    const int row = ew * 32 + lane;  // key index within the tile == TMEM lane; also the query row of dQ_blk
-    const uint32_t lane_base = (uint32_t)(ew * 32) << 16;
-    const int kv = k0 + row;
-    const bool kv_ok = kv < a.M;
-    const uint32_t rowoff = (uint32_t)row * 128u, r7 = (uint32_t)row & 7u;
-    const float sl2 = a.scale * kLog2e;
-    const long long sbase = ((long long)b * a.H + h) * a.N;
-    const int ochunk = a.dpad >> 4;
-    const int C = a.H * a.dh;
-    float* wl = sLD + sw * 4 * W;  // [2W] LSE * log2(e) of this warp's query columns (half 0 then half 1)
-    float* wdv = wl + 2 * W;       // [2W] D * scale
-
-    float nl[NL], nd[NL];
-    auto fetch = [&](int jb) {
-#pragma unroll
-      for (int i = 0; i < NL; ++i) {
-        const int idx = lane + 32 * i;
-        const int qn = jb * BQ + 64 * (idx / W) + cg * W + (idx % W);
-        const bool ok = qn < a.N;
-        nl[i] = ok ? a.LSE[sbase + qn] : INFINITY;  // queries past N: p = 0   (raw values: no use of the loads here,
-        nd[i] = ok ? a.Dv[sbase + qn] : 0.f;        //  so they stay in flight until the next block stages them)
-      }
-    };
-    auto drain_dq = [&](int jb) {
-      mbar_wait(dq_full, (uint32_t)(jb & 1));
-      tc_fence_after();
-      const int qn = jb * BQ + row;
-      float* dst = dQacc + ((long long)b * a.N + qn) * C + h * a.dh;
-      for (int oc = cg; oc < ochunk; oc += CG) {
-        uint32_t v[16];
-        __syncwarp();
-        tmem_ld16(tdQ + lane_base + (uint32_t)(oc * 16), v);
-        tmem_ld_wait();
-        if (qn < a.N) {
-#pragma unroll
-          for (int i = 0; i < 16; i += 4)
-            if (oc * 16 + i < a.dh)
-              red_add_v4(dst + oc * 16 + i, __uint_as_float(v[i]), __uint_as_float(v[i + 1]),
-                         __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
-        }
-      }
-      tc_fence_before();
-      mbar_arrive(dq_empty);
-    };
-
-    fetch(0);
-    for (int j = 0; j < a.nblk; ++j) {
-      __syncwarp();  // every lane is done reading the previous block's staged values
-#pragma unroll
-      for (int i = 0; i < NL; ++i) {
-        wl[lane + 32 * i] = nl[i] * kLog2e;
-        wdv[lane + 32 * i] = nd[i] * a.scale;
-      }
-      __syncwarp();
-      if (j + 1 < a.nblk) fetch(j + 1);  // in flight for the whole block
-      uint8_t* dsb = sdST + (j & 1) * 32768;
-      uint32_t sg[2][G], dg[2][G];
-      mbar_wait(&sp_full[0], (uint32_t)(j & 1));
-      tc_fence_after();
-      __syncwarp();
-      tmem_ldG<G>(tST + lane_base + (uint32_t)(cg * W), sg[0]);
-      tmem_ldG<G>(tdPT + lane_base + (uint32_t)(cg * W), dg[0]);
-#pragma unroll
-      for (int q = 0; q < NG; ++q) {
-        tmem_ld_wait();  // granule q has landed
-        if (q + 1 < NG) {
-          if (q + 1 == GH) {
-            mbar_wait(&sp_full[1], (uint32_t)(j & 1));
-            tc_fence_after();
-          }
-          const uint32_t cn = (uint32_t)(64 * ((q + 1) / GH) + cg * W + ((q + 1) % GH) * G);
-          __syncwarp();
-          tmem_ldG<G>(tST + lane_base + cn, sg[(q + 1) & 1]);
-          tmem_ldG<G>(tdPT + lane_base + cn, dg[(q + 1) & 1]);
-        }
-        const int hf = q / GH;
-        const int cih = cg * W + (q % GH) * G;  // first query column of the granule inside its half
-        const uint32_t* sreg = sg[q & 1];
-        const uint32_t* dp = dg[q & 1];
-        uint32_t wp[G / 2], wd[G / 2];
-#pragma unroll
-        for (int e = 0; e < G / 2; e += 2) {
-          const float4 ls = *reinterpret_cast<const float4*>(&wl[q * G + 2 * e]);
-          const float4 dd = *reinterpret_cast<const float4*>(&wdv[q * G + 2 * e]);
-          const float p0 = ex2_approx(fmaf(__uint_as_float(sreg[2 * e]), sl2, -ls.x));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(sreg[2 * e + 1]), sl2, -ls.y));
-          const float p2 = ex2_approx(fmaf(__uint_as_float(sreg[2 * e + 2]), sl2, -ls.z));
-          const float p3 = ex2_approx(fmaf(__uint_as_float(sreg[2 * e + 3]), sl2, -ls.w));
-          wp[e] = pack_bf16(p0, p1);
-          wp[e + 1] = pack_bf16(p2, p3);
-          wd[e] = pack_bf16(p0 * fmaf(__uint_as_float(dp[2 * e]), a.scale, -dd.x),
-                            p1 * fmaf(__uint_as_float(dp[2 * e + 1]), a.scale, -dd.y));
-          wd[e + 1] = pack_bf16(p2 * fmaf(__uint_as_float(dp[2 * e + 2]), a.scale, -dd.z),
-                                p3 * fmaf(__uint_as_float(dp[2 * e + 3]), a.scale, -dd.w));
-        }
-        if (!kv_ok) {  // keys past M (only in the last key tile): contribute nothing
-#pragma unroll
-          for (int e = 0; e < G / 2; ++e) wp[e] = wd[e] = 0u;
-        }
-        uint8_t* pp = sPT + hf * 16384 + rowoff;
-        uint8_t* pd = dsb + hf * 16384 + rowoff;
-        const uint32_t cb = (uint32_t)(cih >> 3);
-#pragma unroll
-        for (int u = 0; u < G / 8; ++u) {
-          *reinterpret_cast<uint4*>(pp + (((cb + u) ^ r7) << 4)) =
-              make_uint4(wp[4 * u], wp[4 * u + 1], wp[4 * u + 2], wp[4 * u + 3]);
-          *reinterpret_cast<uint4*>(pd + (((cb + u) ^ r7) << 4)) =
-              make_uint4(wd[4 * u], wd[4 * u + 1], wd[4 * u + 2], wd[4 * u + 3]);
-        }
-        if ((q + 1) % GH == 0) {  // this warp's part of half `hf` is in shared memory
-          fence_proxy_async_smem();
-          tc_fence_before();
-          mbar_arrive(&ds_ready[hf]);
-          if (hf == 0 && j > 0) drain_dq(j - 1);
-        }
-      }
-    }
-    drain_dq(a.nblk - 1);
-    mbar_wait(acc_done, (uint32_t)((a.nblk - 1) & 1));
-    tc_fence_after();
-    for (int which = 0; which < 2; ++which) {
-      const uint32_t tacc = which == 0 ? tdV : tdK;
-      bf16* base = which == 0 ? a.dV + (long long)b * a.dv_bs + (long long)kv * a.lddv
-                              : a.dK + (long long)b * a.dk_bs + (long long)kv * a.lddk;
-      for (int oc = cg; oc < ochunk; oc += CG) {
-        const int c = oc * 16;
-        uint32_t v[16];
-        __syncwarp();
-        tmem_ld16(tacc + lane_base + (uint32_t)c, v);
-        tmem_ld_wait();
-        if (kv_ok) {
-          bf16* o = base + h * a.dh + c;
-#pragma unroll
-          for (int i = 0; i < 16; i += 8) {
-            if (c + i < a.dh) {
-              *reinterpret_cast<uint4*>(o + i) =
-                  make_uint4(pack_bf16(__uint_as_float(v[i]), __uint_as_float(v[i + 1])),
-                             pack_bf16(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])),
-                             pack_bf16(__uint_as_float(v[i + 4]), __uint_as_float(v[i + 5])),
-                             pack_bf16(__uint_as_float(v[i + 6]), __uint_as_float(v[i + 7])));
-            }
-          }
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc(tmem, 512);
-  }
-}
-
-// fp32 [B][N][C] -> bf16 with row / batch strides
 __global__ void cvt_dq_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long rows_per_b, int C,
                               long long ldd, long long d_bs, long long total_vec) {
   const int vpr = C / 8;
@@ -1603,6 +1220,14 @@ static int make_head_map(CUtensorMap* m, const void* p, int dh, int H, int rows,
   uint32_t box[4] = {64, 1, (uint32_t)box_rows, 1};
   return e4t_tmap_encode(m, p, 4, dims, str, box, 2);
 }
+int e4t_attn_make_head_map(CUtensorMap* m, const void* p, int dh, int H, int rows, int B, long long ld, long long bs,
+                           int box_rows) {
+  return make_head_map(m, p, dh, H, rows, B, ld, bs, box_rows);
+}
+// two-tile ping-pong forward (attention_fwd2.cu): 1 = launched, 0 = shape outside its envelope, < 0 = error
+int e4t_attn_fwd2_try(const void* Q, const void* K, const void* V, void* O, float* LSE, int B, int H, int N, int M, int dh,
+                      long long ldq, long long q_bs, long long ldk, long long k_bs, long long ldv, long long v_bs,
+                      long long ldo, long long o_bs, float scale, cudaStream_t st);
 static int round16(int x) { return (x + 15) / 16 * 16; }
 // column groups of softmax/dS warps per kernel (0 fwd, 1 dQ, 2 dKV); E4T_ATTN_CG="f,q,k" overrides for tuning
 static int attn_cg(int which) {
@@ -1615,18 +1240,10 @@ static int attn_cg(int which) {
   return cfg[which];
 }
 
-// E4T_ATTN_PP selects the half-tile ping-pong fused backward: 0 = off, 1 = <CG 4, G 8>, 2 = <2, 16>, 3 = <2, 8>,
-// 4 = <4, 16>
-static int attn_pp_mode() {   // read on every call (cheap) so a tuning script can switch variants in-process
-  const char* e = getenv("E4T_ATTN_PP");
-  const int mode = e ? atoi(e) : 0;
-  return (mode < 0 || mode > 4) ? 0 : mode;
-}
-
 static void launch_attn_delta(const void* O, const void* dO, float* Dv, int B, int H, int N, int dh, long long ldo,
                               long long o_bs, long long lddo, long long do_bs, cudaStream_t st) {
-  const char* e = getenv("E4T_ATTN_DELTA2");
-  if (e && atoi(e) != 0)
+  const char* e = getenv("E4T_ATTN_DELTA2");   // default ON since round 2 (thread-per-row; =0 selects the warp-per-row kernel)
+  if (!e || atoi(e) != 0)
     attn_delta2_kernel<<<cdiv((long long)B * N * H, 256), 256, 0, st>>>((const bf16*)O, (const bf16*)dO, Dv, B, H, N, dh,
                                                                         ldo, o_bs, lddo, do_bs);
   else
@@ -1646,6 +1263,14 @@ extern "C" int e4t_attn_fwd(const void* Q, const void* K, const void* V, void* O
                             void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   if (int e = attn_common_checks(dh, ldq, ldk, ldv)) return e;
+  {
+    const int r = e4t_attn_fwd2_try(Q, K, V, O, LSE, B, H, N, M, dh, ldq, q_bs, ldk, k_bs, ldv, v_bs, ldo, o_bs, scale, st);
+    if (r < 0) return e4t_set_error("e4t_attn_fwd: two-tile kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (r == 1) {
+      E4T_COUNT_LAUNCH();
+      return 0;
+    }
+  }
   AttnArgs a;
   memset(&a, 0, sizeof(a));
   a.B = B; a.H = H; a.N = N; a.M = M; a.dh = dh;
@@ -1683,7 +1308,7 @@ extern "C" int e4t_attn_fwd(const void* Q, const void* K, const void* V, void* O
   E4T_CHECK(smem <= (occ2 ? 113 : 227) * 1024, "e4t_attn_fwd: smem budget exceeded (%zu)", smem);
   // opt-in: P through TMEM (needs sbuf*128 + dpad + pbuf*64 columns)
   const char* pte = getenv("E4T_ATTN_FWD_PT");
-  const bool pt = pte && atoi(pte) != 0 && a.sbuf * 128 + a.dpad + a.pbuf * 64 <= a.tmem_cols;
+  const bool pt = (!pte || atoi(pte) != 0) && a.sbuf * 128 + a.dpad + a.pbuf * 64 <= a.tmem_cols;   // default ON
   const dim3 grid(cdiv(N, 128), H, B);
   if (pt) {
     if (occ2) attn_fwd_kernel<2, 2, true><<<grid, 128 + 128 * 2, smem, st>>>(mQ, mK, mV, a);
@@ -1804,10 +1429,6 @@ extern "C" int e4t_attn_bwd_fused(const void* Q, const void* K, const void* V, c
     E4T_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel<4, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     E4T_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel<4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     E4T_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel<4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    E4T_CUDA(cudaFuncSetAttribute(attn_bwd_fused_pp_kernel<4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    E4T_CUDA(cudaFuncSetAttribute(attn_bwd_fused_pp_kernel<2, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    E4T_CUDA(cudaFuncSetAttribute(attn_bwd_fused_pp_kernel<2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    E4T_CUDA(cudaFuncSetAttribute(attn_bwd_fused_pp_kernel<4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr = true;
   }
   AttnArgs a;
@@ -1831,13 +1452,12 @@ extern "C" int e4t_attn_bwd_fused(const void* Q, const void* K, const void* V, c
   a.kst = (fixed + 2 * per_stage <= 227 * 1024 && a.nblk > 1) ? 2 : 1;
   const size_t smem = fixed + a.kst * per_stage;
   E4T_CHECK(smem <= 227 * 1024, "e4t_attn_bwd_fused: smem budget exceeded (%zu)", smem);
-  const int pp = (a.DC == 1 && a.nblk >= 2) ? attn_pp_mode() : 0;
   // opt-in: dQ through a TMA reduce-add (needs 2 x 128 x dh fp32 of extra shared memory: dh <= 64 only)
   const char* dqe = getenv("E4T_ATTN_DQ_TMA");
-  const bool dq_tma = !pp && a.DC == 1 && dqe && atoi(dqe) != 0 && smem + (size_t)2 * 128 * dh * 4 <= 227 * 1024;
+  const bool dq_tma = a.DC == 1 && (!dqe || atoi(dqe) != 0) && smem + (size_t)2 * 128 * dh * 4 <= 227 * 1024;   // default ON
   // opt-in: Pᵀ through TMEM (256 + 3*dpad + 64 columns must fit 512: dpad <= 64)
   const char* pte = getenv("E4T_ATTN_PT_TMEM");
-  const bool pt_tmem = !pp && pte && atoi(pte) != 0 && 256 + 3 * dpad + 64 <= 512;
+  const bool pt_tmem = (!pte || atoi(pte) != 0) && 256 + 3 * dpad + 64 <= 512;   // default ON
   CUtensorMap mDQ;
   memset(&mDQ, 0, sizeof(mDQ));
   if (dq_tma) {
@@ -1846,14 +1466,7 @@ extern "C" int e4t_attn_bwd_fused(const void* Q, const void* K, const void* V, c
     const uint32_t box[3] = {(uint32_t)dh, 128, 1};
     if (int e = e4t_tmap_encode(&mDQ, dQacc, 3, dims, str, box, 4, 0)) return e;
   }
-  if (pp) {   // half-tile ping-pong variant: fixed smem map (see the kernel)
-    const size_t smem_pp = 32768 + 65536 + 32768 + 65536 + 4096 + 256 + 1024;
-    const dim3 grid(cdiv(M, 128), H, B);
-    if (pp == 1) attn_bwd_fused_pp_kernel<4, 8><<<grid, 128 + 128 * 4, smem_pp, st>>>(mQ, mK, mV, mdO, a, dQacc);
-    else if (pp == 2) attn_bwd_fused_pp_kernel<2, 16><<<grid, 128 + 128 * 2, smem_pp, st>>>(mQ, mK, mV, mdO, a, dQacc);
-    else if (pp == 3) attn_bwd_fused_pp_kernel<2, 8><<<grid, 128 + 128 * 2, smem_pp, st>>>(mQ, mK, mV, mdO, a, dQacc);
-    else attn_bwd_fused_pp_kernel<4, 16><<<grid, 128 + 128 * 4, smem_pp, st>>>(mQ, mK, mV, mdO, a, dQacc);
-  } else if (dq_tma && pt_tmem) {
+  if (dq_tma && pt_tmem) {
     attn_bwd_fused_kernel<4, true, true><<<dim3(cdiv(M, 128), H, B), 128 + 128 * 4, smem + 2 * 128 * dh * 4, st>>>(
         mQ, mK, mV, mdO, mDQ, a, dQacc);
   } else if (dq_tma) {

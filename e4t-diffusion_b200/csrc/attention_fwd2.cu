@@ -1,0 +1,390 @@
+// e4t_b200 — attention forward, two-query-tile ping-pong kernel (sm_100a, tcgen05 + TMEM + TMA).
+// Reference call site: F.scaled_dot_product_attention in AttnProcessor2_0 (e4t/models/cross_attention.py:521-531).
+//
+// Why a second forward kernel.  At the level-0 shape of the SD-v1.4 UNet (N = M = 4096, 8 heads x 40) one 128x128 score
+// block needs 16384 exponentials but only ~390 clk of tensor-core time: the kernel is bound by the softmax threads, not
+// by the MMAs.  attn_fwd_kernel (attention.cu) covered the tensor-core/softmax hand-off latency with two CTAs per SM and
+// 16 narrow softmax warps that exchange row maxima through shared memory; ncu showed 26 % of its samples spinning on
+// the S-ready barrier and 17 % in idle role warps.  Here ONE CTA per SM owns TWO 128-query tiles:
+//
+//   warp 0        TMA producer   Q0,Q1 once; K_j / V_j ring (kst stages)
+//   warp 1        MMA issuer     S_t = Q_t K_j^T  and  O_t += P_t V_j  for t = 0,1, interleaved so that the tensor core
+//                                works on tile t while the softmax warps of tile 1-t are busy
+//   warps 4-7     softmax tile 0 one query row per THREAD (TMEM lane == row): the whole 128-wide score row sits in
+//   warps 8-11    softmax tile 1 registers, so there is no cross-thread max exchange, no named barrier, no shuffle
+//
+//   TMEM  S0 [0,128) | S1 [128,256) | O0 [256, 256+dpad) | O1 [.., 256+2 dpad)       (dh <= 128)
+//         P_t (bf16, two per 32-bit column) overwrites columns [0,64) of S_t and is consumed by O_t += P_t V_j as the
+//         TMEM A operand (tcgen05.mma [d], [a], bdesc): P never touches shared memory.  The tensor pipe executes in
+//         issue order, so S_t(j+1) = Q_t K_{j+1}^T, issued after P_t(j) V_j, cannot overwrite P_t(j) early.
+//
+// Softmax details
+//   * lazy rescale with a threshold: the running reference max m only moves when a block's max exceeds it by more than
+//     2^8 (in the exp2 domain); P values may then reach 256, harmless in fp32/bf16.  After the first blocks the O
+//     accumulator is practically never rescaled.
+//   * exp2 split over two pipes (template POLY8 = pairs out of every 8 handled on the FMA pipe): the MUFU unit delivers
+//     16 ex2/clk/SM, i.e. 1024 clk per 128x128 block, 2.6x the tensor time at dh = 40.  The FMA-pipe path is Cody-Waite
+//     range reduction + a degree-3 minimax polynomial (rel. error 7.5e-5, far below bf16 rounding of P) with packed
+//     fma.rn.f32x2 / add.rn.f32x2; the exponent is spliced in with one integer shift-add.
+//   * row max with 3-input max (FMNMX3), scale-and-subtract with packed FFMA2.
+#include "attn_common.cuh"
+#include <stdlib.h>
+
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u64 f2_pack(float lo, float hi) {
+  u64 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(u64 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 f2_fma(u64 a, u64 b, u64 c) {
+  u64 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ u64 f2_add(u64 a, u64 b) {
+  u64 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+      "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]),
+      "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]),
+      "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+
+// 2^x for a PAIR of inputs on the FMA/ALU pipes.  x <= ~8 (threshold rescale) and may be -inf (masked keys).
+//   x  = max(x, -125)                       clamp: the spliced exponent must stay >= 1
+//   t  = x + 1.5*2^23                        low mantissa bits of t = round-to-nearest(x) (two's complement)
+//   f  = x - (t - 1.5*2^23)  in [-0.5, 0.5]
+//   2^f ~ c0 + f (c1 + f (c2 + f c3))        |rel err| < 7.5e-5
+//   result = bits(2^f) + (bits(t) << 23)     adds round(x) to the exponent field
+__device__ __forceinline__ u64 exp2_poly2(u64 x2) {
+  float x0, x1;
+  f2_unpack(x2, x0, x1);
+  x0 = fmaxf(x0, -125.f);
+  x1 = fmaxf(x1, -125.f);
+  const u64 xc = f2_pack(x0, x1);
+  const u64 magic = f2_pack(12582912.f, 12582912.f), nmagic = f2_pack(-12582912.f, -12582912.f);
+  const u64 t2 = f2_add(xc, magic);
+  const u64 xi = f2_add(t2, nmagic);
+  const u64 f2 = f2_fma(xi, f2_pack(-1.f, -1.f), xc);
+  u64 p = f2_fma(f2_pack(0.0551714502f, 0.0551714502f), f2, f2_pack(0.242610843f, 0.242610843f));
+  p = f2_fma(p, f2, f2_pack(0.693260992f, 0.693260992f));
+  p = f2_fma(p, f2, f2_pack(0.999928091f, 0.999928091f));
+  float p0, p1, t0, t1;
+  f2_unpack(p, p0, p1);
+  f2_unpack(t2, t0, t1);
+  const uint32_t r0 = __float_as_uint(p0) + (__float_as_uint(t0) << 23);
+  const uint32_t r1 = __float_as_uint(p1) + (__float_as_uint(t1) << 23);
+  return f2_pack(__uint_as_float(r0), __uint_as_float(r1));
+}
+
+// POLY8: pairs (of every 8 consecutive pairs) whose exp2 runs on the FMA pipe; 0 = all on MUFU.
+template <int POLY8>
+__global__ void __launch_bounds__(384, 1)
+attn_fwd2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                 const __grid_constant__ CUtensorMap mapV, const AttnArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int q_bytes = a.DC * 16384;             // one 128-query tile
+  const int kv_tile = a.DC * 128 * 128;         // one 128-key block of K (or V)
+  uint8_t* sQ = smem;                           // [2 tiles][DC][128][64]
+  uint8_t* sK = sQ + 2 * q_bytes;               // [kst][DC][128][64]
+  uint8_t* sV = sK + a.kst * kv_tile;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + a.kst * kv_tile);
+  uint64_t* q_full = bars;            // [1]
+  uint64_t* k_full = bars + 1;        // [4]
+  uint64_t* k_empty = k_full + 4;     // [4]
+  uint64_t* v_full = k_empty + 4;     // [4]
+  uint64_t* v_empty = v_full + 4;     // [4]
+  uint64_t* s_full = v_empty + 4;     // [2]  MMA -> softmax t : S_t(j) complete (and everything issued before it)
+  uint64_t* p_ready = s_full + 2;     // [2]  softmax t -> MMA : P_t(j) written, O_t rescaled
+  uint64_t* o_done = p_ready + 2;     // [2]  MMA -> softmax t : last P_t V retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 256, h = blockIdx.y, b = blockIdx.z;
+
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_ready[i], 128);
+      mbar_init(&o_done[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapQ);
+    tma_prefetch_desc(&mapK);
+    tma_prefetch_desc(&mapV);
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tO0 = tmem + 256u;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      mbar_expect_tx(q_full, (uint32_t)(2 * q_bytes));
+      for (int t = 0; t < 2; ++t)
+        for (int c = 0; c < a.DC; ++c) tma_load_4d(sQ + t * q_bytes + c * 16384, &mapQ, q_full, c * 64, h, q0 + 128 * t, b);
+    }
+    for (int j = 0; j < a.nblk; ++j) {
+      const int st = j % a.kst;
+      const uint32_t ph = (uint32_t)((j / a.kst) & 1);
+      mbar_wait(&k_empty[st], ph ^ 1u);
+      if (elect_one()) {
+        mbar_expect_tx(&k_full[st], (uint32_t)kv_tile);
+        for (int c = 0; c < a.DC; ++c)
+          tma_load_4d(sK + st * kv_tile + c * 16384, &mapK, &k_full[st], c * 64, h, j * 128, b);
+      }
+      mbar_wait(&v_empty[st], ph ^ 1u);
+      if (elect_one()) {
+        mbar_expect_tx(&v_full[st], (uint32_t)kv_tile);
+        for (int c = 0; c < a.DC; ++c)
+          tma_load_4d(sV + st * kv_tile + c * 16384, &mapV, &v_full[st], c * 64, h, j * 128, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc_s = umma_idesc_bf16(128u, false, false);
+    const uint32_t idesc_o = umma_idesc_bf16((uint32_t)a.dpad, false, true);
+    mbar_wait(q_full, 0);
+    mbar_wait(&k_full[0], 0);
+    tc_fence_after();
+    if (elect_one()) {
+      mma_kmajor(tmem, smem_u32(sQ), 16384, smem_u32(sK), 16384, a.dh, a.DC, idesc_s);
+      umma_commit(&s_full[0]);
+      mma_kmajor(tmem + 128u, smem_u32(sQ + q_bytes), 16384, smem_u32(sK), 16384, a.dh, a.DC, idesc_s);
+      umma_commit(&k_empty[0]);
+      umma_commit(&s_full[1]);
+    }
+    for (int j = 0; j < a.nblk; ++j) {
+      const int st = j % a.kst;
+      const int jn = j + 1, stn = jn % a.kst;
+      const bool more = jn < a.nblk;
+      for (int t = 0; t < 2; ++t) {
+        mbar_wait(&p_ready[t], (uint32_t)(j & 1));
+        if (t == 0) {
+          mbar_wait(&v_full[st], (uint32_t)((j / a.kst) & 1));
+          if (more) mbar_wait(&k_full[stn], (uint32_t)((jn / a.kst) & 1));
+        }
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t tS = tmem + (uint32_t)t * 128u;
+          mma_pv_ts(tO0 + (uint32_t)(t * a.dpad), tS, smem_u32(sV + st * kv_tile), 16384, 128, idesc_o, j > 0 ? 1u : 0u);
+          if (t == 1) umma_commit(&v_empty[st]);
+          if (more) {
+            mma_kmajor(tS, smem_u32(sQ + t * q_bytes), 16384, smem_u32(sK + stn * kv_tile), 16384, a.dh, a.DC, idesc_s);
+            if (t == 1) umma_commit(&k_empty[stn]);
+            umma_commit(&s_full[t]);
+          } else {
+            umma_commit(&o_done[t]);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== softmax warps: tile t = (warp - 4) / 4, one query row per thread =====================
+    const int t = (warp - 4) >> 2;
+    const int ew = warp & 3;                       // TMEM lane quadrant this warp may access
+    const int row = ew * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(ew * 32) << 16;
+    const uint32_t tS = tmem + (uint32_t)t * 128u + lane_base;
+    const uint32_t tO = tO0 + (uint32_t)(t * a.dpad) + lane_base;
+    const float sl2 = a.scale * kLog2e;
+    const u64 sl2_2 = f2_pack(sl2, sl2);
+    const int ochunk = a.dpad >> 4;
+    float m = -INFINITY;                           // reference max of this row (raw score units)
+    float l0 = 0.f, l1 = 0.f;
+    for (int j = 0; j < a.nblk; ++j) {
+      mbar_wait(&s_full[t], (uint32_t)(j & 1));
+      tc_fence_after();
+      uint32_t v[128];
+      tmem_ld32(tS, v);
+      tmem_ld32(tS + 32u, v + 32);
+      tmem_ld32(tS + 64u, v + 64);
+      tmem_ld32(tS + 96u, v + 96);
+      tmem_ld_wait();
+      const int kv0 = j * 128;
+      if (kv0 + 128 > a.M) {                       // ragged last block: keys >= M are masked out
+#pragma unroll
+        for (int e = 0; e < 128; ++e)
+          if (kv0 + e >= a.M) v[e] = 0xff800000u;  // -inf
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int e = 0; e < 128; e += 4) {
+        mx0 = max3(mx0, __uint_as_float(v[e]), __uint_as_float(v[e + 1]));
+        mx1 = max3(mx1, __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+      }
+      const float mx = fmaxf(mx0, mx1);
+      // move the reference max only when this block exceeds it by more than 2^8 in the exp2 domain
+      const bool need = (mx - m) * sl2 > 8.f;      // m = -inf on the first block -> true
+      if (__any_sync(0xffffffffu, need)) {
+        const float m_new = need ? mx : m;
+        const float alpha = ex2_approx((m - m_new) * sl2);   // 1 for rows that keep their max; 0 on the first block
+        l0 *= alpha;
+        l1 *= alpha;
+        m = m_new;
+        if (j > 0) {   // O_t holds P V of blocks < j (complete: s_full(j) was committed after P_t(j-1) V)
+          for (int oc = 0; oc < ochunk; ++oc) {
+            uint32_t ov[16];
+            tmem_ld16(tO + (uint32_t)(oc * 16), ov);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) ov[e] = __float_as_uint(__uint_as_float(ov[e]) * alpha);
+            tmem_st16(tO + (uint32_t)(oc * 16), ov);
+          }
+        }
+      }
+      const float nmb = -m * sl2;
+      const u64 nmb2 = f2_pack(nmb, nmb);
+      u64 ls = f2_pack(0.f, 0.f);
+#pragma unroll
+      for (int e = 0; e < 64; ++e) {               // pair e = columns 2e, 2e+1
+        const u64 x2 = f2_fma(f2_pack(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1])), sl2_2, nmb2);
+        u64 p2;
+        if ((e & 7) < POLY8) {
+          p2 = exp2_poly2(x2);
+        } else {
+          float x0, x1;
+          f2_unpack(x2, x0, x1);
+          p2 = f2_pack(ex2_approx(x0), ex2_approx(x1));
+        }
+        ls = f2_add(ls, p2);
+        float p0, p1;
+        f2_unpack(p2, p0, p1);
+        v[e] = pack_bf16(p0, p1);
+      }
+      {
+        float s0, s1;
+        f2_unpack(ls, s0, s1);
+        l0 += s0;
+        l1 += s1;
+      }
+      // P_t -> TMEM columns [0,64) of S_t (A operand of O_t += P_t V)
+      tmem_st32(tS, v);
+      tmem_st32(tS + 32u, v + 32);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&p_ready[t]);
+    }
+    // ---- epilogue: normalise and store this tile's rows ----
+    mbar_wait(&o_done[t], 0);
+    tc_fence_after();
+    const float lt = l0 + l1;
+    const float inv_l = 1.f / lt;
+    const int n = q0 + 128 * t + row;
+    for (int oc = 0; oc < ochunk; ++oc) {
+      const int c = oc * 16;
+      uint32_t ov[16];
+      tmem_ld16(tO + (uint32_t)c, ov);
+      tmem_ld_wait();
+      if (n < a.N) {
+        bf16* o = a.O + (long long)b * a.o_bs + (long long)n * a.ldo + h * a.dh + c;
+#pragma unroll
+        for (int i = 0; i < 16; i += 8) {
+          if (c + i < a.dh) {
+            *reinterpret_cast<uint4*>(o + i) =
+                make_uint4(pack_bf16(__uint_as_float(ov[i]) * inv_l, __uint_as_float(ov[i + 1]) * inv_l),
+                           pack_bf16(__uint_as_float(ov[i + 2]) * inv_l, __uint_as_float(ov[i + 3]) * inv_l),
+                           pack_bf16(__uint_as_float(ov[i + 4]) * inv_l, __uint_as_float(ov[i + 5]) * inv_l),
+                           pack_bf16(__uint_as_float(ov[i + 6]) * inv_l, __uint_as_float(ov[i + 7]) * inv_l));
+          }
+        }
+      }
+    }
+    if (n < a.N) a.LSE[((long long)b * a.H + h) * a.N + n] = m * a.scale + logf(lt);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host
+// ---------------------------------------------------------------------------------------------
+int e4t_attn_make_head_map(CUtensorMap* m, const void* p, int dh, int H, int rows, int B, long long ld, long long bs,
+                           int box_rows);
+
+// Returns 1 if this kernel took the call, 0 if the shape is outside its envelope (caller falls back), <0 on error.
+int e4t_attn_fwd2_try(const void* Q, const void* K, const void* V, void* O, float* LSE, int B, int H, int N, int M, int dh,
+                      long long ldq, long long q_bs, long long ldk, long long k_bs, long long ldv, long long v_bs,
+                      long long ldo, long long o_bs, float scale, cudaStream_t st) {
+  const char* e = getenv("E4T_ATTN_FWD2");      // "0" disables; "p<k>" / "<k>" selects POLY8 = k
+  int poly8 = 0;
+  if (e) {
+    if (e[0] == '0' && e[1] == 0) return 0;
+    poly8 = atoi(e[0] == 'p' ? e + 1 : e) & 7;
+    if (e[0] != 'p' && atoi(e) == 1) poly8 = 0;
+  }
+  if (dh > 128 || M < 128 || N < 128) return 0;
+  AttnArgs a;
+  memset(&a, 0, sizeof(a));
+  a.B = B; a.H = H; a.N = N; a.M = M; a.dh = dh;
+  a.DC = cdiv(dh, 64);
+  a.dpad = (dh + 15) / 16 * 16;
+  a.BKV = 128;
+  a.nblk = cdiv(M, 128);
+  a.scale = scale;
+  a.O = (bf16*)O; a.ldo = ldo; a.o_bs = o_bs; a.LSE = LSE;
+  const size_t fixed = (size_t)2 * a.DC * 16384 + 512 + 1024;
+  const size_t per_stage = (size_t)2 * a.DC * 16384;
+  int kst = (int)((227 * 1024 - fixed) / per_stage);
+  if (kst > 4) kst = 4;
+  if (kst > a.nblk) kst = a.nblk;
+  if (kst < 1) return 0;
+  a.kst = kst;
+  const size_t smem = fixed + (size_t)kst * per_stage;
+  CUtensorMap mQ, mK, mV;
+  if (e4t_attn_make_head_map(&mQ, Q, dh, H, N, B, ldq, q_bs, 128)) return -1;
+  if (e4t_attn_make_head_map(&mK, K, dh, H, M, B, ldk, k_bs, 128)) return -1;
+  if (e4t_attn_make_head_map(&mV, V, dh, H, M, B, ldv, v_bs, 128)) return -1;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(attn_fwd2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(attn_fwd2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(attn_fwd2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(attn_fwd2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    attr = true;
+  }
+  const dim3 grid(cdiv(N, 256), H, B);
+  switch (poly8) {
+    case 2: attn_fwd2_kernel<2><<<grid, 384, smem, st>>>(mQ, mK, mV, a); break;
+    case 3: attn_fwd2_kernel<3><<<grid, 384, smem, st>>>(mQ, mK, mV, a); break;
+    case 4: attn_fwd2_kernel<4><<<grid, 384, smem, st>>>(mQ, mK, mV, a); break;
+    default: attn_fwd2_kernel<0><<<grid, 384, smem, st>>>(mQ, mK, mV, a); break;
+  }
+  if (cudaGetLastError() != cudaSuccess) return -1;
+  return 1;
+}

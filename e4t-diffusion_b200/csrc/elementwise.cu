@@ -757,10 +757,14 @@ __global__ void wo_bank_outer_kernel(const WOProj* __restrict__ tab) {
     const int r = (int)((i * 4) / n), c = (int)((i * 4) % n);
     const float ur = u[r], tr = t ? t[r] : 0.f;
     const float4 wv = *reinterpret_cast<const float4*>(w + c);
-    *reinterpret_cast<float4*>(dM + i * 4) = make_float4(ur * wv.x + tr, ur * wv.y + tr, ur * wv.z + tr, ur * wv.w + tr);
+    // ACCUMULATE into the .grad view (zeroed by zero_grad): several backward passes before an optimiser step
+    // (gradient accumulation, accelerator.accumulate in pretrain_e4t.py:595) add up like torch's AccumulateGrad
+    float4 g = *reinterpret_cast<const float4*>(dM + i * 4);
+    g.x += ur * wv.x + tr; g.y += ur * wv.y + tr; g.z += ur * wv.z + tr; g.w += ur * wv.w + tr;
+    *reinterpret_cast<float4*>(dM + i * 4) = g;
   }
 }
-// backward 4: vector grads (dw1, db1, dw2, db2, dv) and the copies dbr = G1, dbc = GTs.  one block per projection
+// backward 4: vector grads (dw1, db1, dw2, db2, dv) and dbr += G1, dbc += GTs (accumulating).  one block per projection
 __global__ void wo_bank_vec_kernel(const WOProj* __restrict__ tab) {
   const WOProj p = tab[blockIdx.x];
   __shared__ float red[32];
@@ -771,16 +775,16 @@ __global__ void wo_bank_vec_kernel(const WOProj* __restrict__ tab) {
   float acc = 0.f;
   for (int j = threadIdx.x; j < R; j += blockDim.x) {
     const float d = dvx[j];
-    p.dw1[j] = d * vv;
-    p.db1[j] = d;
-    p.dbc[j] = GTs[j];
+    p.dw1[j] += d * vv;
+    p.db1[j] += d;
+    p.dbc[j] += GTs[j];
     acc += p.w1[j] * d;
   }
   for (int j = threadIdx.x; j < C; j += blockDim.x) {
     const float d = dvy[j];
-    p.dw2[j] = d * vv;
-    p.db2[j] = d;
-    p.dbr[j] = G1[j];
+    p.dw2[j] += d * vv;
+    p.db2[j] += d;
+    p.dbr[j] += G1[j];
     acc += p.w2[j] * d;
   }
   acc = warp_sum(acc);
@@ -789,7 +793,7 @@ __global__ void wo_bank_vec_kernel(const WOProj* __restrict__ tab) {
   if (threadIdx.x < 32) {
     float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
     t = warp_sum(t);
-    if (threadIdx.x == 0) p.dv[0] = t;
+    if (threadIdx.x == 0) p.dv[0] += t;
   }
 }
 // tab: device array of n WOProj records; max_r / max_c: largest row/column dims in the bank.

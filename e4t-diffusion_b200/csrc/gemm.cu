@@ -34,7 +34,7 @@ struct GemmArgs {
   float alpha;
   int debug;      // E4T_GEMM_DEBUG bit0: skip epilogue body; bit1: skip tmem loads only
   int tma_store;  // bf16 output through smem staging + TMA store (coalesced, asynchronous)
-  int epi_plain;  // opt-in (E4T_GEMM_EPI_PLAIN=1): separate slab loop for outputs without alpha/bias/rowgroup/residual
+  int epi_plain;  // default on (E4T_GEMM_EPI_PLAIN=0 disables): separate slab loop for outputs without alpha/bias/rowgroup/residual
 };
 
 static constexpr int kBM = 128;
@@ -427,12 +427,18 @@ static int num_sms() {
   return g_num_sms;
 }
 
-// Tile-width choice by a small cost model (cycles per SM):
-//   per 64-deep k-chunk a CTA needs max(MMA, smem operand reads) = max(2*BN, 128+BN) cycles
-//   (tcgen05 128xBNx16 = BN/2 cycles, 4 per chunk; smem feeds (128+BN)*128 B per chunk at 128 B/cycle);
-//   the epilogue of a tile overlaps the next tile's mainloop, so a tile costs max(mainloop, epilogue) plus a fixed
-//   pipeline bubble; the persistent grid runs ceil(tiles / SMs) rounds.
-static int pick_bn(int N, long m_tiles_x_batch, bool b_mn, int force_bn, int kchunks_per_tile = 16) {
+// Tile-width choice by a cost model FITTED to measurements (tools/sweep_r2.py gemm: every GEMM/conv signature of the
+// pre-training step timed at every BN on a B200, profiles/r02_gemm_bn_sweep.md; rms log-error of the fit 9.5 %).
+// In nominal cycles per CTA:
+//   mainloop per 64-deep k-chunk  = 505 + 0.47 * BN   (operand delivery dominates: the cost is almost flat in BN, so the
+//                                                      widest tile that does not add a round of the persistent grid wins)
+//   epilogue per tile             = 2060 + 21.6 * BN * (1 + 1.07 * [residual]) * (6 if fp32 atomics)
+//   tile                          = max(mainloop, epilogue)   (the epilogue of tile i overlaps the mainloop of i+1)
+//   kernel                        = ceil(tiles / SMs) * tile + epilogue
+// Choosing BN with this model costs 39.1 ms/step over the 116 signatures, against 38.8 ms for the per-signature best and
+// 44.4 ms for the round-1 model (max(2*BN, 128+BN) per chunk), which preferred tiles that were too narrow.
+static int pick_bn(int N, long m_tiles_x_batch, bool b_mn, int force_bn, int kchunks_per_tile = 16,
+                   bool residual = false, bool atomic = false) {
   if (force_bn > 0) return force_bn;
   const int step = b_mn ? 64 : 32;
   int best = 0;
@@ -441,10 +447,9 @@ static int pick_bn(int N, long m_tiles_x_batch, bool b_mn, int force_bn, int kch
   for (int bn = 256; bn >= 64; bn -= step) {
     const int tiles_n = cdiv(N, bn);
     const double tiles = (double)tiles_n * (double)m_tiles_x_batch;
-    const double chunk = (2.0 * bn > 128.0 + bn) ? 2.0 * bn : 128.0 + bn;
-    const double mainloop = kchunks_per_tile * chunk;
-    const double epilogue = 250.0 + 6.0 * bn;
-    const double tile = (mainloop > epilogue ? mainloop : epilogue) + 150.0;
+    const double mainloop = kchunks_per_tile * (505.0 + 0.47 * bn);
+    const double epilogue = 2060.0 + 21.6 * bn * (residual ? 2.07 : 1.0) * (atomic ? 6.0 : 1.0);
+    const double tile = mainloop > epilogue ? mainloop : epilogue;
     const double rounds = (double)((long)((tiles + sms - 1) / sms));
     const double cost = rounds * tile + epilogue;
     if (cost < best_cost - 1e-6) {
@@ -463,8 +468,8 @@ static int launch_gemm(const CUtensorMap& mA, const CUtensorMap& mB, GemmArgs& g
   {
     const char* d = getenv("E4T_GEMM_DEBUG");
     g.debug = d ? atoi(d) : 0;
-    const char* p = getenv("E4T_GEMM_EPI_PLAIN");
-    g.epi_plain = p ? atoi(p) : 0;
+    const char* p = getenv("E4T_GEMM_EPI_PLAIN");   // default ON (bit-identical on all 40 step signatures, r02 sweep)
+    g.epi_plain = p ? atoi(p) : 1;
   }
   static int use_tma_store = -1;
   if (use_tma_store < 0) {
@@ -520,7 +525,7 @@ extern "C" int e4t_gemm_bf16(const void* A, const void* B, void* out, int M, int
   if (splits > g.kchunks) splits = g.kchunks;
   g.kper = cdiv(g.kchunks, splits);
   g.splits = cdiv(g.kchunks, g.kper);  // no empty split
-  g.BN = pick_bn(N, (long)g.m_tiles * batch * g.splits, b_mn != 0, force_bn, g.kper);
+  g.BN = pick_bn(N, (long)g.m_tiles * batch * g.splits, b_mn != 0, force_bn, g.kper, residual != nullptr, out_mode == 2);
   E4T_CHECK(g.BN >= 32 && g.BN <= 256 && (g.BN % (b_mn ? 64 : 32)) == 0, "e4t_gemm_bf16: bad BN %d", g.BN);
   g.n_tiles = cdiv(N, g.BN);
   E4T_CHECK(g.splits == 1 || out_mode == 2, "e4t_gemm_bf16: split-K requires atomic fp32 output");
@@ -590,7 +595,7 @@ extern "C" int e4t_conv3x3_bf16(const void* x, const void* w, void* out, int B, 
   g.m_tiles = cdiv(g.M, kBM);
   g.kchunks = 9 * g.cin_chunks;
   g.kper = g.kchunks; g.splits = 1;
-  g.BN = pick_bn(Cout, g.m_tiles, false, force_bn, g.kchunks);
+  g.BN = pick_bn(Cout, g.m_tiles, false, force_bn, g.kchunks, residual != nullptr, false);
   g.n_tiles = cdiv(Cout, g.BN);
   g.out = out; g.out_mode = out_mode; g.ldo = Cout; g.out_bstride = 0;
   g.bias = bias; g.rowgroup = rowgroup; g.rows_per_group = img;

@@ -170,9 +170,24 @@ class E4TEncoder(ModelMixin, ConfigMixin):
         return out
 
     def _stacked(self):
+        """(n,W,W) / (n,W) views over the per-layer parameters.  When an arena optimiser (FlatAdamW) has re-homed the
+        parameters, they are still laid out back to back inside its arena (it moves each shared storage as one block):
+        the stacked tensors are rebuilt as strided VIEWS of that memory — never copied out of the arena, which would
+        detach the parameters from the optimiser's updates."""
         l0 = self.first_linears[0].weight
         if l0.data_ptr() != self._fl_w.data_ptr() or l0.device != self._fl_w.device:
-            self._restack_first_linears()
+            n, W = len(self.first_linears), l0.shape[0]
+            b0 = self.first_linears[0].bias
+            es = l0.element_size()
+            contiguous = all(l.weight.data_ptr() == l0.data_ptr() + i * W * W * es
+                             and l.bias.data_ptr() == b0.data_ptr() + i * W * es
+                             and l.weight.is_contiguous() and l.bias.is_contiguous()
+                             for i, l in enumerate(self.first_linears))
+            if contiguous:
+                self._fl_w = torch.as_strided(l0.data, (n, W, W), (W * W, W, 1))
+                self._fl_b = torch.as_strided(b0.data, (n, W), (W, 1))
+            else:
+                self._restack_first_linears()
         return self._fl_w, self._fl_b
 
     def preprocess(self, x):

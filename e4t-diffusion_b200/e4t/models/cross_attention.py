@@ -83,6 +83,33 @@ class CrossAttention(nn.Module):
         h = self.heads
         return tensor.reshape(bh // h, h, n, d).permute(0, 2, 1, 3).reshape(bh // h, n, d * h)
 
+    def get_attention_scores(self, query, key, attention_mask=None):
+        """softmax(scale * Q Kᵀ (+ mask)) on head-batched (B*H, N, dh) tensors — the materialising helper of the
+        non-fused processors (cross_attention.py:222-251).  The fused processor never calls it (scores do not leave
+        the SM there); it is part of the module surface other processors / visualisation code rely on."""
+        dtype = query.dtype
+        if self.upcast_attention:
+            query, key = query.float(), key.float()
+        scores = torch.matmul(query, key.transpose(-1, -2)) * self.scale
+        if attention_mask is not None:
+            scores = scores + attention_mask
+        if self.upcast_softmax:
+            scores = scores.float()
+        return scores.softmax(dim=-1).to(dtype)
+
+    def prepare_attention_mask(self, attention_mask, target_length, batch_size=None):
+        """Pad the mask by `target_length` zeros on the key axis and repeat it per head
+        (cross_attention.py:253-282; batch_size=None is the deprecated 1-sample form)."""
+        if batch_size is None:
+            batch_size = 1
+        if attention_mask is None:
+            return None
+        if attention_mask.shape[-1] != target_length:
+            attention_mask = torch.nn.functional.pad(attention_mask, (0, target_length), value=0.0)
+        if attention_mask.shape[0] < batch_size * self.heads:
+            attention_mask = attention_mask.repeat_interleave(self.heads, dim=0)
+        return attention_mask
+
     def forward(self, hidden_states, encoder_hidden_states=None, attention_mask=None, **cross_attention_kwargs):
         return self.processor(self, hidden_states, encoder_hidden_states=encoder_hidden_states,
                               attention_mask=attention_mask, **cross_attention_kwargs)

@@ -229,6 +229,8 @@ class UNet2DConditionModel(ModelMixin, ConfigMixin):
             raise NotImplementedError("attention_mask / class_labels / ControlNet residuals are not on the E4T path")
         if any(s % (2 ** self.num_upsamplers) != 0 for s in sample.shape[-2:]):
             raise NotImplementedError("latent size must be a multiple of 2**num_upsamplers")
+        if not torch.is_grad_enabled():
+            FN.bump_nograd_fwd_epoch()      # no-grad forwards always rebuild W_eff from the current parameters
         if self.config.center_input_sample:
             sample = 2 * sample - 1.0
         B = sample.shape[0]

@@ -49,24 +49,78 @@ def load_e4t_unet(pretrained_model_name_or_path=None, ckpt_path=None, **kwargs):
     with open(os.path.join(d, "config.json")) as f:
         cfg = {k: v for k, v in json.load(f).items() if not k.startswith("_")}
     unet = UNet2DConditionModel(**cfg)
-    state_dict = {}
-    for name in ("diffusion_pytorch_model.bin",):
-        if os.path.exists(os.path.join(d, name)):
-            state_dict.update(torch.load(os.path.join(d, name), map_location="cpu"))
+    state_dict = _load_diffusers_weights(d)
+    if not state_dict:
+        # the reference goes through OriginalUNet2DConditionModel.from_pretrained (utils.py:114) and therefore always
+        # starts from real base weights; a directory without a weight file must not silently mean "random init"
+        raise FileNotFoundError(f"no UNet weights under {d} (looked for diffusion_pytorch_model.{{bin,safetensors}} "
+                                f"and their sharded *.index.json forms)")
     if ckpt_path:
         state_dict.update(torch.load(ckpt_path, map_location="cpu"))
         print(f"Resuming from {ckpt_path}")
     m, u = unet.load_state_dict(state_dict, strict=False)
-    if len(m) > 0 and ckpt_path:
+    if ckpt_path is None:
+        m = [k for k in m if "wo" not in k]      # a fresh run starts its WeightOffsets from their default init
+    if len(m) > 0:
         raise RuntimeError(f"missing keys:\n{m}")
     if len(u) > 0:
         raise RuntimeError(f"unexpected keys:\n{u}")
     return unet
 
 
-def save_e4t_unet(model, save_dir):
+def _load_diffusers_weights(d, stem="diffusion_pytorch_model"):
+    """state dict of a diffusers-format model directory: <stem>.bin / <stem>.safetensors or the sharded
+    <stem>.{bin,safetensors}.index.json forms."""
+    state_dict = {}
+
+    def load_one(path):
+        if path.endswith(".safetensors"):
+            from safetensors.torch import load_file
+            return load_file(path, device="cpu")
+        return torch.load(path, map_location="cpu")
+
+    for ext in ("safetensors", "bin"):
+        single = os.path.join(d, f"{stem}.{ext}")
+        index = single + ".index.json"
+        if os.path.exists(single):
+            state_dict.update(load_one(single))
+            break
+        if os.path.exists(index):
+            with open(index) as f:
+                shards = sorted(set(json.load(f)["weight_map"].values()))
+            for sh in shards:
+                state_dict.update(load_one(os.path.join(d, sh)))
+            break
+    return state_dict
+
+
+def _detached(sd):
+    """Clones: after FlatAdamW the trainable parameters are views of one 1.5 GB arena, and torch.save serialises the
+    whole storage behind every view."""
+    return {k: v.detach().clone().contiguous() for k, v in sd.items()}
+
+
+def save_e4t_unet(model, save_dir, save_all=False):
+    """weight_offsets.pt = the "wo" entries (utils.py:129-131); save_all=True -> unet.pt = the full state dict
+    (tuning_e4t.py:232)."""
     os.makedirs(save_dir, exist_ok=True)
-    torch.save({k: v for k, v in model.state_dict().items() if "wo" in k}, os.path.join(save_dir, "weight_offsets.pt"))
+    if save_all:
+        torch.save(_detached(model.state_dict()), os.path.join(save_dir, "unet.pt"))
+    else:
+        torch.save(_detached({k: v for k, v in model.state_dict().items() if "wo" in k}),
+                   os.path.join(save_dir, "weight_offsets.pt"))
+
+
+def save_config(args, save_dir, pretrained_args=None):
+    """config.json as the training scripts write it (pretrain_e4t.py:230-234; nested `pretrained_args` when a run
+    starts from an earlier E4T checkpoint, utils.py:76-89)."""
+    os.makedirs(save_dir, exist_ok=True)
+    cfg = dict(vars(args)) if not isinstance(args, dict) else dict(args)
+    if pretrained_args is not None:
+        cfg["pretrained_args"] = dict(pretrained_args)
+    with open(os.path.join(save_dir, "config.json"), "w", encoding="utf-8") as f:
+        json.dump(cfg, f, indent=2, default=str)
+    return cfg
 
 
 def load_e4t_encoder(ckpt_path=None, **kwargs):
@@ -88,7 +142,7 @@ def load_e4t_encoder(ckpt_path=None, **kwargs):
 
 def save_e4t_encoder(model, save_dir):
     os.makedirs(save_dir, exist_ok=True)
-    torch.save(model.state_dict(), os.path.join(save_dir, "encoder.pt"))
+    torch.save(_detached(model.state_dict()), os.path.join(save_dir, "encoder.pt"))
 
 
 def image_grid(imgs, rows, cols):
@@ -99,3 +153,24 @@ def image_grid(imgs, rows, cols):
     for i, img in enumerate(imgs):
         grid.paste(img, box=(i % cols * w, i // cols * h))
     return grid
+
+
+def load_image(image_path, resolution=None):
+    """PIL RGB image from a local path or URL; with `resolution`, the shorter side is resized to it (Lanczos,
+    albumentations.SmallestMaxSize(interpolation=3) in the reference) and the centre square is cropped
+    (utils.py:162-177)."""
+    from PIL import Image, ImageOps
+    if image_path.startswith("http://") or image_path.startswith("https://"):
+        import requests
+        img = Image.open(requests.get(image_path, stream=True).raw)
+    else:
+        img = Image.open(image_path)
+    img = ImageOps.exif_transpose(img).convert("RGB")
+    if resolution:
+        w, h = img.size
+        s = resolution / min(w, h)
+        img = img.resize((max(resolution, round(w * s)), max(resolution, round(h * s))), resample=Image.LANCZOS)
+        w, h = img.size
+        left, top = (w - resolution) // 2, (h - resolution) // 2
+        img = img.crop((left, top, left + resolution, top + resolution))
+    return img

@@ -110,6 +110,26 @@ class FlatAdamW:
         FN.bump_param_epoch()
 
 
+    # ---- checkpoint / resume (pretrain_e4t.py:536-558 resumes optimizer state through accelerator.load_state) ------
+    def state_dict(self):
+        """Moments and step count (clones, not arena views).  Parameters themselves travel in weight_offsets.pt /
+        encoder.pt; `numel` guards against loading into a differently laid-out arena."""
+        return dict(numel=self.numel, step=self.step_count, exp_avg=self.exp_avg.detach().clone(),
+                    exp_avg_sq=self.exp_avg_sq.detach().clone(), lr=self.lr, betas=self.betas,
+                    weight_decay=self.weight_decay, eps=self.eps)
+
+    def load_state_dict(self, sd):
+        if int(sd["numel"]) != self.numel:
+            raise ValueError(f"optimizer arena size mismatch: checkpoint {sd['numel']} vs {self.numel}")
+        self.exp_avg.copy_(sd["exp_avg"])
+        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        self.step_count = int(sd["step"])
+        self.step_dev.fill_(self.step_count)
+        for k in ("lr", "betas", "weight_decay", "eps"):
+            if k in sd:
+                setattr(self, k, tuple(sd[k]) if k == "betas" else sd[k])
+
+
 def trainable_parameters(unet, e4t_encoder):
     """optim_params of pretrain_e4t.py:274-278: encoder params with requires_grad + UNet params whose name has 'wo'."""
     ps = [p for p in e4t_encoder.parameters() if p.requires_grad]
@@ -230,6 +250,7 @@ class PretrainStep:
             for k, v in batch.items():
                 self._static[k].copy_(v, non_blocking=True)
             self._graph.replay()
+            FN.bump_param_epoch()        # the replayed AdamW moved the parameters behind torch's version counters
             if not self._graph_has_opt:
                 self._apply_optimizer()
             return dict(self._static_out)

@@ -24,6 +24,14 @@ def bump_param_epoch():
     PARAM_EPOCH += 1
 
 
+NOGRAD_FWD_EPOCH = 0  # bumped by every no-grad UNet forward: W_eff is then always rebuilt from the current parameters
+
+
+def bump_nograd_fwd_epoch():
+    global NOGRAD_FWD_EPOCH
+    NOGRAD_FWD_EPOCH += 1
+
+
 def prepared(param, key, fn):
     """Cached derived tensor of a parameter (e.g. its bf16 / re-laid-out copy), refreshed on version change."""
     cache = getattr(param, "_e4t_prep", None)
@@ -311,7 +319,6 @@ class WOEffectiveFn(torch.autograd.Function):
             r0 += W.shape[0]
             saved += [vx, vy, a, b, s]
         ctx.n = n
-        ctx.params = args[n:]     # python refs to the leaf parameters (for direct gradient writes)
         ctx.save_for_backward(*args, *saved)
         carrier = torch.empty((Ctot, R), device=out.device, dtype=F32)
         ctx.mark_non_differentiable(out)
@@ -333,16 +340,11 @@ class WOEffectiveFn(torch.autograd.Function):
             v, w1, b1, w2, b2, Wc, bc, Wr, br = p
             vx, vy, a, b, s = fac[5 * i:5 * i + 5]
             C = W.shape[0]
-            plist = ctx.params[9 * i:9 * i + 9]
-            if DIRECT_GRAD_WRITE and all(getattr(q, "_e4t_arena", False) and q.grad is not None for q in plist):
-                outs = [q.grad.view(-1) if q.grad.dim() != 2 else q.grad for q in plist]
-                outs[1] = plist[1].grad.view(-1); outs[3] = plist[3].grad.view(-1)
-                ops.wo_bwd(dW[r0:r0 + C], W, v, w1, w2, Wc, Wr, bc, vx, vy, a, b, s, outs=outs)
-                grads += [None] * 9
-            else:
-                dv, dw1, db1, dw2, db2, dWc, dbc, dWr, dbr = ops.wo_bwd(dW[r0:r0 + C], W, v, w1, w2, Wc, Wr, bc, vx,
-                                                                      vy, a, b, s)
-                grads += [dv, dw1.view_as(w1), db1, dw2.view_as(w2), db2, dWc, dbc, dWr, dbr]
+            # gradients are RETURNED (autograd's AccumulateGrad adds them to .grad, arena view or not), so repeated
+            # backward passes before an optimiser step accumulate; the batched WOBank path accumulates in its kernels
+            dv, dw1, db1, dw2, db2, dWc, dbc, dWr, dbr = ops.wo_bwd(dW[r0:r0 + C], W, v, w1, w2, Wc, Wr, bc, vx,
+                                                                  vy, a, b, s)
+            grads += [dv, dw1.view_as(w1), db1, dw2.view_as(w2), db2, dWc, dbc, dWr, dbr]
             r0 += C
         return (None,) + (None,) * n + tuple(grads)
 

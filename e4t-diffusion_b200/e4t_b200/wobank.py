@@ -78,6 +78,8 @@ class WOBank:
         self._token = None
         self._key = None
         assert _lib.load().e4t_wo_bank_record_size() == ctypes.sizeof(_WOProj)
+        for m in self.modules:      # any (partial) load_state_dict invalidates the cached W_eff
+            m.register_load_state_dict_post_hook(lambda mod, keys: FN.bump_param_epoch())
 
     # ---- device table -------------------------------------------------------------------------------------------
     def _signature(self):
@@ -122,7 +124,10 @@ class WOBank:
     def get(self, module, group):
         """(W_eff view, dW_eff accumulation view, autograd token) for one attention module's projection group."""
         grad_on = torch.is_grad_enabled()
-        key = (FN.PARAM_EPOCH, FN.WO_EPOCH if grad_on else -1, grad_on, tuple(p._version for p in self.params[:9]))
+        # no-grad calls (sampling at log steps, inference) rebuild W_eff once per UNet forward: a CUDA-graph replay
+        # or a partial load_state_dict moves the parameters without telling this cache (ADVICE r1)
+        key = (FN.PARAM_EPOCH, FN.WO_EPOCH if grad_on else -1, grad_on, 0 if grad_on else FN.NOGRAD_FWD_EPOCH,
+               tuple(p._version for p in self.params[:9]))
         if self._key != key:
             if grad_on:
                 self._token = _BankFn.apply(self, *self.params)

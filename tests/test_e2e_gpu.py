@@ -204,3 +204,93 @@ def test_cuda_graph_step_matches_eager():
     print("[graph] eager", la, "graph", lb)
     for x, y in zip(la, lb):
         assert abs(x - y) <= 2e-3 * abs(x) + 1e-5
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# the REAL configuration: SD-v1.4 UNet + E4T encoder with CLIP ViT-H/14 + CLIP-L text (BASELINE.json configs[0]/[1] model)
+# --------------------------------------------------------------------------------------------------------------------
+def _grad_errs(named, gold):
+    errs = {}
+    for k, ref in gold.items():
+        if k.endswith("#corner"):
+            g = named[k[:-7]].grad
+            got = g.reshape(g.shape[0], -1)[:16, :16]
+        elif k.endswith("#norm"):
+            got = named[k[:-5]].grad.norm()
+        else:
+            got = named[k].grad
+        errs[k] = _rel(got, ref)
+    return errs
+
+
+def test_pretrain_step_sd14_vith_vs_reference_golden():
+    """Whole step at the real model sizes against tests/golden/step_sd14_vith.pt (oracle/gen_golden_step.py: the
+    reference's own UNet modules, transformers.CLIPVisionModel at ViT-H/14 size, fp32 CPU): step-0 prediction, domain
+    embedding, EVERY WeightOffsets gradient including the 96 `.v` scalars, encoder-head gradients, integer token
+    bookkeeping (bit-exact) and the loss curve of a 10-step AdamW run (a different seeded batch every step)."""
+    from e4t.encoder import E4TEncoder
+    from e4t.models.modeling_clip import CLIPTextConfig, CLIPTextModel
+    from e4t_b200.engine import PretrainStep
+    gold = torch.load(os.path.join(GOLD, "step_sd14_vith.pt"))
+    ucfg, vcfg, tcfg = gold["cfg"]["unet"], gold["cfg"]["vit"], gold["cfg"]["text"]
+    su, se, st = gold["seeds"]
+    B = gold["B"]
+    unet, _ = _build_unet(ucfg, su)
+    enc = E4TEncoder(arch="ViT-H-14", word_embedding_dim=tcfg["width"])
+    enc.load_state_dict(O.synth_state_dict(O.encoder_param_shapes(vcfg, 10880, tcfg["width"], 129), se), strict=True)
+    text = CLIPTextModel(CLIPTextConfig(vocab_size=tcfg["vocab"], hidden_size=tcfg["width"],
+                                        intermediate_size=tcfg["mlp"], num_hidden_layers=tcfg["layers"],
+                                        num_attention_heads=tcfg["heads"]))
+    text.load_state_dict(O.synth_state_dict(O.text_param_shapes(tcfg), st), strict=True)
+    step = PretrainStep(unet, enc.cuda(), text.cuda(), O.PLACEHOLDER_ID, class_token_id=gold["class_token_id"],
+                        lr=gold["lr"], weight_dtype=torch.bfloat16)
+    arena_lo = step.opt.arena.data_ptr()
+    arena_hi = arena_lo + step.opt.arena.numel() * 4
+    fl0 = enc.first_linears[3].weight.detach().clone()
+    losses = []
+    for it, ref_l in enumerate(gold["losses"]):
+        gb = {k: v.cuda() for k, v in O.synth_batch(B, seed=gold["batch_seed0"] + it).items()}
+        out = step.forward_loss(gb)
+        out["loss"].backward()
+        if it == 0:
+            assert out["placeholder_idxs"] == gold["placeholder_idxs"]          # bit-exact integer bookkeeping
+            e_pred = _rel(out["pred"], gold["pred"])
+            e_dom = _rel(out["domain_embed"], gold["domain_embed"])
+            named_u, named_e = dict(unet.named_parameters()), dict(enc.named_parameters())
+            eu = _grad_errs(named_u, gold["wo_grads"])
+            eh = _grad_errs(named_e, gold["head_grads"])
+            vec = sorted(v for k, v in eu.items() if not k.endswith(".v"))
+            # the 96 `.v` scalars: dv = w1.dβ1 + w2.dβ2 is a cancelling sum; its error is measured against the size of
+            # the summed terms (gold["v_scale"]), i.e. as a backward error — and the sign must agree wherever the
+            # reference gradient is not itself below that noise floor
+            ev, sign_bad = [], 0
+            for k, sc in gold["v_scale"].items():
+                got, ref = named_u[k].grad.item(), gold["wo_grads"][k].item()
+                ev.append(abs(got - ref) / sc.item())
+                if abs(ref) > 0.05 * sc.item() and got * ref < 0:
+                    sign_bad += 1
+            all_v_got = torch.stack([named_u[k].grad.reshape(()) for k in gold["v_scale"]])
+            all_v_ref = torch.stack([gold["wo_grads"][k].reshape(()) for k in gold["v_scale"]])
+            print(f"[sd14+vith] pred {e_pred:.3e} domain_embed {e_dom:.3e} | wo grads median {vec[len(vec)//2]:.3e} "
+                  f"max {vec[-1]:.3e} | .v backward-error median {sorted(ev)[len(ev)//2]:.3e} max {max(ev):.3e} "
+                  f"vector rel {_rel(all_v_got, all_v_ref):.3e} sign flips {sign_bad} | head grads max "
+                  f"{max(eh.values()):.3e} ({max(eh, key=eh.get)})")
+            assert e_pred < 3e-2 and e_dom < 3e-2
+            assert vec[len(vec) // 2] < 6e-2 and vec[-1] < 0.2
+            assert max(ev) < 5e-2 and sign_bad == 0
+            assert max(eh.values()) < 8e-2
+        losses.append([out[k].item() for k in ("loss", "loss_diff", "loss_reg")])
+        scale = step.opt.all_reduce_grads()
+        step.opt.step(scale)
+        step.opt.zero_grad()
+    # ADVICE r1 (high): the stacked first_linears must stay inside the optimiser's arena and must be updated by it
+    w = enc.first_linears[3].weight
+    assert arena_lo <= w.data_ptr() < arena_hi and arena_lo <= enc._stacked()[0].data_ptr() < arena_hi
+    assert not torch.equal(w.detach(), fl0)
+    print("[sd14+vith] loss curve reference:", [round(l[0], 4) for l in gold["losses"]])
+    print("[sd14+vith] loss curve cuda     :", [round(l[0], 4) for l in losses])
+    print("[sd14+vith] loss_reg  reference:", [round(l[2], 5) for l in gold["losses"]])
+    print("[sd14+vith] loss_reg  cuda     :", [round(l[2], 5) for l in losses])
+    for lo, lg in zip(gold["losses"], losses):
+        assert abs(lo[0] - lg[0]) <= 3e-2 * abs(lo[0]) + 1e-4, (lo, lg)
+        assert abs(lo[2] - lg[2]) <= 5e-2 * abs(lo[2]) + 1e-5, (lo, lg)
