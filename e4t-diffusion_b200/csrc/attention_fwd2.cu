@@ -95,7 +95,13 @@ __device__ __forceinline__ u64 exp2_poly2(u64 x2) {
 }
 
 // POLY8: pairs (of every 8 consecutive pairs) whose exp2 runs on the FMA pipe; 0 = all on MUFU.
-template <int POLY8>
+// F16P : P is produced by ex2.approx.f16x2 — ONE MUFU operation per PAIR of scores (measured on B200,
+//        tools/micro/pipe_rates.cu: 0.5 warp-instructions/clk/SM for both the f32 and the f16x2 form, i.e. the packed
+//        form doubles the exponential rate to 32/clk/SM) — and stays fp16: the A operand of O += P V is then fp16 (10
+//        mantissa bits, finer than the bf16 P of the other variants) against a bf16 B operand; fp16's range is ample
+//        because p <= 2^8 with the threshold rescale.  The argument of the exponential is rounded to fp16 first
+//        (|x| < 8 -> absolute error <= 2^-9, i.e. <= 0.14 % on p, the same order as bf16 rounding of p itself).
+template <int POLY8, bool F16P>
 __global__ void __launch_bounds__(384, 1)
 attn_fwd2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                  const __grid_constant__ CUtensorMap mapV, const AttnArgs a) {
@@ -173,7 +179,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     const uint32_t idesc_s = umma_idesc_bf16(128u, false, false);
-    const uint32_t idesc_o = umma_idesc_bf16((uint32_t)a.dpad, false, true);
+    // O += P V: A = P from TMEM (bf16, or fp16 when F16P: a_format field, bits 7-9, = 0), B = V (bf16, MN-major)
+    const uint32_t idesc_o = umma_idesc_bf16((uint32_t)a.dpad, false, true) & (F16P ? ~(7u << 7) : ~0u);
     mbar_wait(q_full, 0);
     mbar_wait(&k_full[0], 0);
     tc_fence_after();
@@ -223,6 +230,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
     const int ochunk = a.dpad >> 4;
     float m = -INFINITY;                           // reference max of this row (raw score units)
     float l0 = 0.f, l1 = 0.f;
+    if (a.pbuf && t == 1) asm volatile("bar.arrive 2, 256;" ::: "memory");   // tile 0 owns the first exp phase
     for (int j = 0; j < a.nblk; ++j) {
       mbar_wait(&s_full[t], (uint32_t)(j & 1));
       tc_fence_after();
@@ -266,26 +274,51 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
       }
       const float nmb = -m * sl2;
       const u64 nmb2 = f2_pack(nmb, nmb);
-      u64 ls = f2_pack(0.f, 0.f);
+      // exp-phase token: the two softmax warpgroups take turns on the MUFU pipe, so that the tensor-core work of tile t
+      // (P_t V, then S_t of the next block) always runs under the exponentials of tile 1-t instead of both
+      // warpgroups finishing together and then both waiting for the tensor core
+      if (a.pbuf) {
+        if (t == 0) asm volatile("bar.sync 2, 256;" ::: "memory");
+        else asm volatile("bar.sync 3, 256;" ::: "memory");
+      }
+      u64 ls = f2_pack(0.f, 0.f), ls2 = f2_pack(0.f, 0.f);
 #pragma unroll
       for (int e = 0; e < 64; ++e) {               // pair e = columns 2e, 2e+1
         const u64 x2 = f2_fma(f2_pack(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1])), sl2_2, nmb2);
         u64 p2;
-        if ((e & 7) < POLY8) {
-          p2 = exp2_poly2(x2);
-        } else {
+        if constexpr (F16P) {
           float x0, x1;
           f2_unpack(x2, x0, x1);
-          p2 = f2_pack(ex2_approx(x0), ex2_approx(x1));
+          uint32_t hx, he;
+          asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hx) : "f"(x1), "f"(x0));
+          asm("ex2.approx.f16x2 %0, %1;" : "=r"(he) : "r"(hx));
+          float p0, p1;
+          asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tcvt.f32.f16 %0, lo;\n\tcvt.f32.f16 %1, hi;\n\t}"
+              : "=f"(p0), "=f"(p1) : "r"(he));
+          p2 = f2_pack(p0, p1);
+          v[e] = he;
+        } else {
+          if ((e & 7) < POLY8) {
+            p2 = exp2_poly2(x2);
+          } else {
+            float x0, x1;
+            f2_unpack(x2, x0, x1);
+            p2 = f2_pack(ex2_approx(x0), ex2_approx(x1));
+          }
+          float p0, p1;
+          f2_unpack(p2, p0, p1);
+          v[e] = pack_bf16(p0, p1);
         }
-        ls = f2_add(ls, p2);
-        float p0, p1;
-        f2_unpack(p2, p0, p1);
-        v[e] = pack_bf16(p0, p1);
+        if (e & 1) ls2 = f2_add(ls2, p2);
+        else ls = f2_add(ls, p2);
+      }
+      if (a.pbuf && !(t == 1 && j == a.nblk - 1)) {   // hand the token to the other warpgroup
+        if (t == 0) asm volatile("bar.arrive 3, 256;" ::: "memory");
+        else asm volatile("bar.arrive 2, 256;" ::: "memory");
       }
       {
         float s0, s1;
-        f2_unpack(ls, s0, s1);
+        f2_unpack(f2_add(ls, ls2), s0, s1);
         l0 += s0;
         l1 += s1;
       }
@@ -341,12 +374,17 @@ int e4t_attn_make_head_map(CUtensorMap* m, const void* p, int dh, int H, int row
 int e4t_attn_fwd2_try(const void* Q, const void* K, const void* V, void* O, float* LSE, int B, int H, int N, int M, int dh,
                       long long ldq, long long q_bs, long long ldk, long long k_bs, long long ldv, long long v_bs,
                       long long ldo, long long o_bs, float scale, cudaStream_t st) {
-  const char* e = getenv("E4T_ATTN_FWD2");      // "0" disables; "p<k>" / "<k>" selects POLY8 = k
-  int poly8 = 0;
+  // E4T_ATTN_FWD2: "0" disables this kernel; otherwise a string of flags: 'p<k>' FMA-pipe exp2 for k of every 8 pairs,
+  // 'h' fp16 P through ex2.approx.f16x2, 'n' no exp-phase token (both warpgroups free-running)
+  const char* e = getenv("E4T_ATTN_FWD2");
+  int poly8 = 0, f16p = 0, token = 1;
   if (e) {
     if (e[0] == '0' && e[1] == 0) return 0;
-    poly8 = atoi(e[0] == 'p' ? e + 1 : e) & 7;
-    if (e[0] != 'p' && atoi(e) == 1) poly8 = 0;
+    for (const char* c = e; *c; ++c) {
+      if (*c == 'p' && c[1] >= '0' && c[1] <= '7') poly8 = c[1] - '0';
+      if (*c == 'h') f16p = 1;
+      if (*c == 'n') token = 0;
+    }
   }
   if (dh > 128 || M < 128 || N < 128) return 0;
   AttnArgs a;
@@ -357,6 +395,7 @@ int e4t_attn_fwd2_try(const void* Q, const void* K, const void* V, void* O, floa
   a.BKV = 128;
   a.nblk = cdiv(M, 128);
   a.scale = scale;
+  a.pbuf = token;     // (field reused) 1 = exp-phase token ping-pong between the two softmax warpgroups
   a.O = (bf16*)O; a.ldo = ldo; a.o_bs = o_bs; a.LSE = LSE;
   const size_t fixed = (size_t)2 * a.DC * 16384 + 512 + 1024;
   const size_t per_stage = (size_t)2 * a.DC * 16384;
@@ -372,18 +411,20 @@ int e4t_attn_fwd2_try(const void* Q, const void* K, const void* V, void* O, floa
   if (e4t_attn_make_head_map(&mV, V, dh, H, M, B, ldv, v_bs, 128)) return -1;
   static bool attr = false;
   if (!attr) {
-    cudaFuncSetAttribute(attn_fwd2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(attn_fwd2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(attn_fwd2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(attn_fwd2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(attn_fwd2_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(attn_fwd2_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(attn_fwd2_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(attn_fwd2_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(attn_fwd2_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     attr = true;
   }
   const dim3 grid(cdiv(N, 256), H, B);
-  switch (poly8) {
-    case 2: attn_fwd2_kernel<2><<<grid, 384, smem, st>>>(mQ, mK, mV, a); break;
-    case 3: attn_fwd2_kernel<3><<<grid, 384, smem, st>>>(mQ, mK, mV, a); break;
-    case 4: attn_fwd2_kernel<4><<<grid, 384, smem, st>>>(mQ, mK, mV, a); break;
-    default: attn_fwd2_kernel<0><<<grid, 384, smem, st>>>(mQ, mK, mV, a); break;
+  if (f16p) attn_fwd2_kernel<0, true><<<grid, 384, smem, st>>>(mQ, mK, mV, a);
+  else switch (poly8) {
+    case 2: attn_fwd2_kernel<2, false><<<grid, 384, smem, st>>>(mQ, mK, mV, a); break;
+    case 3: attn_fwd2_kernel<3, false><<<grid, 384, smem, st>>>(mQ, mK, mV, a); break;
+    case 4: attn_fwd2_kernel<4, false><<<grid, 384, smem, st>>>(mQ, mK, mV, a); break;
+    default: attn_fwd2_kernel<0, false><<<grid, 384, smem, st>>>(mQ, mK, mV, a); break;
   }
   if (cudaGetLastError() != cudaSuccess) return -1;
   return 1;

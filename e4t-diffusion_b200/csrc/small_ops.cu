@@ -1,0 +1,355 @@
+// e4t_b200 — small HBM-bound / short-sequence operators (sm_100a) that complete the E4T step on hand-written kernels:
+//   * GELU / quick-GELU forward and backward           (open_clip ViT MLP `nn.GELU`, encoder.py:91-96; HF CLIP text
+//                                                        `quick_gelu`, modeling_clip.py:10-82 via CLIPEncoderLayer)
+//   * LeakyReLU forward / backward                      (E4TEncoder head, encoder.py:101-105,163-166)
+//   * column sum  dbias[n] = sum_m dY[m][n]             (bias gradients of every trainable Linear / conv)
+//   * short-sequence attention with optional causal mask (N, M <= 128, dh <= 64): the CLIP text tower's 77-token
+//     causal self-attention (modeling_clip.py:45-51).  One CTA per (batch, head); Q/K/V/dO live in shared memory as
+//     bf16, the score matrix as fp32.  At 77 x 77 x 64 the whole tower's attention is 0.3 GFLOP per step: latency,
+//     not throughput, is what matters, and a 128-row tcgen05 tile would be 40 % padding.
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// activations (bf16 in / out, fp32 math); mode 0 = exact erf GELU, 1 = quick GELU x*sigmoid(1.702x), 2 = LeakyReLU(0.01)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float act_f(float x, int mode) {
+  if (mode == 0) return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
+  if (mode == 1) return x / (1.f + __expf(-1.702f * x));
+  return x > 0.f ? x : 0.01f * x;
+}
+__device__ __forceinline__ float act_df(float x, int mode) {
+  if (mode == 0) {
+    const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752f));
+    return cdf + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+  }
+  if (mode == 1) {
+    const float s = 1.f / (1.f + __expf(-1.702f * x));
+    return s * (1.f + 1.702f * x * (1.f - s));
+  }
+  return x > 0.f ? 1.f : 0.01f;
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(256) act_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy,
+                                                  bf16* __restrict__ out, long long nvec, int mode) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 u = reinterpret_cast<const uint4*>(x)[i];
+    const uint32_t us[4] = {u.x, u.y, u.z, u.w};
+    uint32_t ds[4] = {0, 0, 0, 0};
+    if (BWD) {
+      const uint4 d = reinterpret_cast<const uint4*>(dy)[i];
+      ds[0] = d.x; ds[1] = d.y; ds[2] = d.z; ds[3] = d.w;
+    }
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 v = unpack_bf16(us[j]);
+      if (BWD) {
+        const float2 g = unpack_bf16(ds[j]);
+        o[j] = pack_bf16(g.x * act_df(v.x, mode), g.y * act_df(v.y, mode));
+      } else {
+        o[j] = pack_bf16(act_f(v.x, mode), act_f(v.y, mode));
+      }
+    }
+    reinterpret_cast<uint4*>(out)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+extern "C" int e4t_act_fwd(const void* x, void* y, long long n, int mode, void* stream_) {
+  E4T_CHECK(n % 8 == 0 && mode >= 0 && mode <= 2, "e4t_act_fwd: n %% 8 != 0 or bad mode");
+  const long long nvec = n / 8;
+  long long blocks = (nvec + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) return 0;
+  act_kernel<false><<<(int)blocks, 256, 0, (cudaStream_t)stream_>>>((const bf16*)x, nullptr, (bf16*)y, nvec, mode);
+  E4T_COUNT_LAUNCH();
+  E4T_LAUNCH_CHECK();
+  return 0;
+}
+extern "C" int e4t_act_bwd(const void* x, const void* dy, void* dx, long long n, int mode, void* stream_) {
+  E4T_CHECK(n % 8 == 0 && mode >= 0 && mode <= 2, "e4t_act_bwd: n %% 8 != 0 or bad mode");
+  const long long nvec = n / 8;
+  long long blocks = (nvec + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) return 0;
+  act_kernel<true><<<(int)blocks, 256, 0, (cudaStream_t)stream_>>>((const bf16*)x, (const bf16*)dy, (bf16*)dx, nvec, mode);
+  E4T_COUNT_LAUNCH();
+  E4T_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// column sum: out[n] += sum_m X[m][n]   (X bf16 [M][ld], out fp32 [N], accumulating -> usable directly on .grad)
+// block = 32 x 8 threads: each thread owns 8 consecutive columns (one 16-byte load), the 8 thread-rows stride over m
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ X, float* __restrict__ out, long long M,
+                                                     int N, long long ld, int rows_per_block) {
+  __shared__ float red[8][256 + 8];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n0 = (blockIdx.x * 32 + tx) * 8;
+  const long long m0 = (long long)blockIdx.y * rows_per_block;
+  long long m1 = m0 + rows_per_block;
+  if (m1 > M) m1 = M;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (n0 < N) {
+    for (long long m = m0 + ty; m < m1; m += 8) {
+      const uint4 u = *reinterpret_cast<const uint4*>(X + m * ld + n0);
+      const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+      acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
+      acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[ty][tx * 8 + j] = acc[j];
+  __syncthreads();
+  const int c = threadIdx.x;   // 256 columns of this block
+  float s = 0.f;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) s += red[r][c];
+  const int n = blockIdx.x * 256 + c;
+  if (n < N) atomicAdd(out + n, s);
+}
+extern "C" int e4t_colsum_acc(const void* X, float* out, long long M, int N, long long ld, void* stream_) {
+  E4T_CHECK(N % 8 == 0 && ld % 8 == 0, "e4t_colsum_acc: N and ld must be multiples of 8");
+  if (M <= 0) return 0;
+  const int gx = cdiv(N, 256);
+  long long gy = (148 * 4 + gx - 1) / gx;
+  int rpb = (int)((M + gy - 1) / gy);
+  if (rpb < 64) rpb = 64;
+  gy = (M + rpb - 1) / rpb;
+  colsum_kernel<<<dim3(gx, (unsigned)gy), 256, 0, (cudaStream_t)stream_>>>((const bf16*)X, out, M, N, ld, rpb);
+  E4T_COUNT_LAUNCH();
+  E4T_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// short-sequence attention (N, M <= 128, dh <= 64, dh % 8 == 0), optional causal mask (key j > query i masked)
+// ---------------------------------------------------------------------------------------------
+static constexpr int kSA_MAX = 128;      // max sequence
+static constexpr int kSA_LD = 64 + 8;    // bf16 row pitch of the Q/K/V/dO tiles (72: 16-byte aligned rows, spreads banks)
+static constexpr int kSA_PLD = kSA_MAX + 1;
+
+struct SmallAttnArgs {
+  const bf16 *Q, *K, *V, *O, *dO;
+  bf16 *Out, *dQ, *dK, *dV;
+  float* LSE;
+  int B, H, N, M, dh, causal;
+  long long ldq, q_bs, ldk, k_bs, ldv, v_bs, ldo, o_bs, lddo, do_bs, lddq, dq_bs, lddk, dk_bs, lddv, dv_bs;
+  float scale;
+};
+
+__device__ __forceinline__ void sa_load_tile(bf16* s, const bf16* g, int rows, int dh, long long ld) {
+  const int vpr = dh / 8;
+  for (int i = threadIdx.x; i < rows * vpr; i += blockDim.x) {
+    const int r = i / vpr, c = (i % vpr) * 8;
+    *reinterpret_cast<uint4*>(s + r * kSA_LD + c) = *reinterpret_cast<const uint4*>(g + (long long)r * ld + c);
+  }
+}
+__device__ __forceinline__ float sa_dot(const bf16* a, const bf16* b, int dh) {
+  float acc = 0.f;
+  for (int d = 0; d < dh; d += 8) {
+    const uint4 x = *reinterpret_cast<const uint4*>(a + d), y = *reinterpret_cast<const uint4*>(b + d);
+    const uint32_t xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 p = unpack_bf16(xs[j]), q = unpack_bf16(ys[j]);
+      acc += p.x * q.x + p.y * q.y;
+    }
+  }
+  return acc;
+}
+
+// scores + softmax into sP (fp32 [N][kSA_PLD]); returns with sP = P (normalised); row LSE written to lse_out if given
+__device__ __forceinline__ void sa_scores_softmax(float* sP, const bf16* sQ, const bf16* sK, const SmallAttnArgs& a,
+                                                  float* lse_out, const float* lse_in) {
+  const int N = a.N, M = a.M;
+  for (int idx = threadIdx.x; idx < N * M; idx += blockDim.x) {
+    const int i = idx / M, j = idx % M;
+    float s = -INFINITY;
+    if (!a.causal || j <= i) s = sa_dot(sQ + i * kSA_LD, sK + j * kSA_LD, a.dh) * a.scale;
+    sP[i * kSA_PLD + j] = s;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int i = warp; i < N; i += nw) {
+    float* row = sP + i * kSA_PLD;
+    float lse;
+    if (lse_in) {
+      lse = lse_in[i];
+    } else {
+      float mx = -INFINITY;
+      for (int j = lane; j < M; j += 32) mx = fmaxf(mx, row[j]);
+      mx = warp_max(mx);
+      float sum = 0.f;
+      for (int j = lane; j < M; j += 32) sum += __expf(row[j] - mx);
+      sum = warp_sum(sum);
+      lse = mx + logf(sum);
+      if (lse_out && lane == 0) lse_out[i] = lse;
+    }
+    for (int j = lane; j < M; j += 32) row[j] = __expf(row[j] - lse);   // masked entries: exp(-inf) = 0
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) attn_small_fwd_kernel(const SmallAttnArgs a) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  bf16* sQ = reinterpret_cast<bf16*>(sm);
+  bf16* sK = sQ + kSA_MAX * kSA_LD;
+  bf16* sV = sK + kSA_MAX * kSA_LD;
+  float* sP = reinterpret_cast<float*>(sV + kSA_MAX * kSA_LD);
+  const int h = blockIdx.x, b = blockIdx.y;
+  sa_load_tile(sQ, a.Q + b * a.q_bs + h * a.dh, a.N, a.dh, a.ldq);
+  sa_load_tile(sK, a.K + b * a.k_bs + h * a.dh, a.M, a.dh, a.ldk);
+  sa_load_tile(sV, a.V + b * a.v_bs + h * a.dh, a.M, a.dh, a.ldv);
+  __syncthreads();
+  sa_scores_softmax(sP, sQ, sK, a, a.LSE + ((long long)b * a.H + h) * a.N, nullptr);
+  // O[i][d] = sum_j P[i][j] V[j][d]; thread -> (i, pair of d)
+  const int dp = a.dh / 2;
+  for (int idx = threadIdx.x; idx < a.N * dp; idx += blockDim.x) {
+    const int i = idx / dp, d = (idx % dp) * 2;
+    const float* pr = sP + i * kSA_PLD;
+    float o0 = 0.f, o1 = 0.f;
+    const int jmax = a.causal ? min(a.M, i + 1) : a.M;
+    for (int j = 0; j < jmax; ++j) {
+      const float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(sV + j * kSA_LD + d));
+      o0 += pr[j] * v.x;
+      o1 += pr[j] * v.y;
+    }
+    *reinterpret_cast<uint32_t*>(a.Out + b * a.o_bs + (long long)i * a.ldo + h * a.dh + d) = pack_bf16(o0, o1);
+  }
+}
+
+__global__ void __launch_bounds__(256) attn_small_bwd_kernel(const SmallAttnArgs a) {
+  extern __shared__ __align__(16) uint8_t sm[];
+  bf16* sQ = reinterpret_cast<bf16*>(sm);
+  bf16* sK = sQ + kSA_MAX * kSA_LD;
+  bf16* sV = sK + kSA_MAX * kSA_LD;
+  bf16* sdO = sV + kSA_MAX * kSA_LD;
+  float* sP = reinterpret_cast<float*>(sdO + kSA_MAX * kSA_LD);
+  float* sdS = sP + kSA_MAX * kSA_PLD;
+  float* sD = sdS + kSA_MAX * kSA_PLD;     // [N] rowsum(dO * O)
+  float* sL = sD + kSA_MAX;                // [N] LSE
+  const int h = blockIdx.x, b = blockIdx.y;
+  const int N = a.N, M = a.M, dh = a.dh;
+  sa_load_tile(sQ, a.Q + b * a.q_bs + h * dh, N, dh, a.ldq);
+  sa_load_tile(sK, a.K + b * a.k_bs + h * dh, M, dh, a.ldk);
+  sa_load_tile(sV, a.V + b * a.v_bs + h * dh, M, dh, a.ldv);
+  sa_load_tile(sdO, a.dO + b * a.do_bs + h * dh, N, dh, a.lddo);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int i = warp; i < N; i += nw) {   // D_i = sum_d dO[i][d] O[i][d]
+    const bf16* o = a.O + b * a.o_bs + (long long)i * a.ldo + h * dh;
+    const bf16* d = a.dO + b * a.do_bs + (long long)i * a.lddo + h * dh;
+    float acc = 0.f;
+    for (int c = lane * 2; c < dh; c += 64) {
+      const float2 x = unpack_bf16(*reinterpret_cast<const uint32_t*>(o + c));
+      const float2 y = unpack_bf16(*reinterpret_cast<const uint32_t*>(d + c));
+      acc += x.x * y.x + x.y * y.y;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      sD[i] = acc;
+      sL[i] = a.LSE[((long long)b * a.H + h) * N + i];
+    }
+  }
+  __syncthreads();
+  sa_scores_softmax(sP, sQ, sK, a, nullptr, sL);
+  // dS[i][j] = P (dP - D) * scale, dP[i][j] = dO[i] . V[j]
+  for (int idx = threadIdx.x; idx < N * M; idx += blockDim.x) {
+    const int i = idx / M, j = idx % M;
+    const float p = sP[i * kSA_PLD + j];
+    float ds = 0.f;
+    if (p != 0.f) ds = p * (sa_dot(sdO + i * kSA_LD, sV + j * kSA_LD, dh) - sD[i]) * a.scale;
+    sdS[i * kSA_PLD + j] = ds;
+  }
+  __syncthreads();
+  const int dp = dh / 2;
+  // dQ[i][d] = sum_j dS[i][j] K[j][d]
+  for (int idx = threadIdx.x; idx < N * dp; idx += blockDim.x) {
+    const int i = idx / dp, d = (idx % dp) * 2;
+    const float* r = sdS + i * kSA_PLD;
+    float o0 = 0.f, o1 = 0.f;
+    const int jmax = a.causal ? min(M, i + 1) : M;
+    for (int j = 0; j < jmax; ++j) {
+      const float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(sK + j * kSA_LD + d));
+      o0 += r[j] * v.x;
+      o1 += r[j] * v.y;
+    }
+    *reinterpret_cast<uint32_t*>(a.dQ + b * a.dq_bs + (long long)i * a.lddq + h * dh + d) = pack_bf16(o0, o1);
+  }
+  // dK[j][d] = sum_i dS[i][j] Q[i][d];  dV[j][d] = sum_i P[i][j] dO[i][d]
+  for (int idx = threadIdx.x; idx < M * dp; idx += blockDim.x) {
+    const int j = idx / dp, d = (idx % dp) * 2;
+    float k0 = 0.f, k1 = 0.f, v0 = 0.f, v1 = 0.f;
+    const int i0 = a.causal ? j : 0;
+    for (int i = i0; i < N; ++i) {
+      const float ds = sdS[i * kSA_PLD + j], p = sP[i * kSA_PLD + j];
+      const float2 q = unpack_bf16(*reinterpret_cast<const uint32_t*>(sQ + i * kSA_LD + d));
+      const float2 g = unpack_bf16(*reinterpret_cast<const uint32_t*>(sdO + i * kSA_LD + d));
+      k0 += ds * q.x; k1 += ds * q.y;
+      v0 += p * g.x;  v1 += p * g.y;
+    }
+    *reinterpret_cast<uint32_t*>(a.dK + b * a.dk_bs + (long long)j * a.lddk + h * dh + d) = pack_bf16(k0, k1);
+    *reinterpret_cast<uint32_t*>(a.dV + b * a.dv_bs + (long long)j * a.lddv + h * dh + d) = pack_bf16(v0, v1);
+  }
+}
+
+static int sa_checks(int N, int M, int dh, long long ldq, long long ldk, long long ldv) {
+  E4T_CHECK(N >= 1 && M >= 1 && N <= kSA_MAX && M <= kSA_MAX, "e4t_attn_small: N, M must be in [1, 128] (got %d, %d)", N, M);
+  E4T_CHECK(dh % 8 == 0 && dh >= 8 && dh <= 64, "e4t_attn_small: head dim %d unsupported (dh %% 8 == 0, <= 64)", dh);
+  E4T_CHECK(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0, "e4t_attn_small: row strides must be multiples of 8 elements");
+  return 0;
+}
+
+extern "C" int e4t_attn_small_fwd(const void* Q, const void* K, const void* V, void* O, float* LSE, int B, int H, int N,
+                                  int M, int dh, long long ldq, long long q_bs, long long ldk, long long k_bs,
+                                  long long ldv, long long v_bs, long long ldo, long long o_bs, float scale, int causal,
+                                  void* stream_) {
+  if (int e = sa_checks(N, M, dh, ldq, ldk, ldv)) return e;
+  SmallAttnArgs a;
+  memset(&a, 0, sizeof(a));
+  a.Q = (const bf16*)Q; a.K = (const bf16*)K; a.V = (const bf16*)V; a.Out = (bf16*)O; a.LSE = LSE;
+  a.B = B; a.H = H; a.N = N; a.M = M; a.dh = dh; a.causal = causal;
+  a.ldq = ldq; a.q_bs = q_bs; a.ldk = ldk; a.k_bs = k_bs; a.ldv = ldv; a.v_bs = v_bs; a.ldo = ldo; a.o_bs = o_bs;
+  a.scale = scale;
+  const size_t smem = (size_t)3 * kSA_MAX * kSA_LD * 2 + (size_t)kSA_MAX * kSA_PLD * 4;
+  static bool attr = false;
+  if (!attr) {
+    E4T_CUDA(cudaFuncSetAttribute(attn_small_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  attn_small_fwd_kernel<<<dim3(H, B), 256, smem, (cudaStream_t)stream_>>>(a);
+  E4T_COUNT_LAUNCH();
+  E4T_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int e4t_attn_small_bwd(const void* Q, const void* K, const void* V, const void* O, const void* dO,
+                                  const float* LSE, void* dQ, void* dK, void* dV, int B, int H, int N, int M, int dh,
+                                  long long ldq, long long q_bs, long long ldk, long long k_bs, long long ldv,
+                                  long long v_bs, long long ldo, long long o_bs, long long lddo, long long do_bs,
+                                  long long lddq, long long dq_bs, long long lddk, long long dk_bs, long long lddv,
+                                  long long dv_bs, float scale, int causal, void* stream_) {
+  if (int e = sa_checks(N, M, dh, ldq, ldk, ldv)) return e;
+  E4T_CHECK(lddo % 8 == 0, "e4t_attn_small_bwd: dO row stride must be a multiple of 8 elements");
+  SmallAttnArgs a;
+  memset(&a, 0, sizeof(a));
+  a.Q = (const bf16*)Q; a.K = (const bf16*)K; a.V = (const bf16*)V; a.O = (const bf16*)O; a.dO = (const bf16*)dO;
+  a.LSE = const_cast<float*>(LSE);
+  a.dQ = (bf16*)dQ; a.dK = (bf16*)dK; a.dV = (bf16*)dV;
+  a.B = B; a.H = H; a.N = N; a.M = M; a.dh = dh; a.causal = causal;
+  a.ldq = ldq; a.q_bs = q_bs; a.ldk = ldk; a.k_bs = k_bs; a.ldv = ldv; a.v_bs = v_bs; a.ldo = ldo; a.o_bs = o_bs;
+  a.lddo = lddo; a.do_bs = do_bs; a.lddq = lddq; a.dq_bs = dq_bs; a.lddk = lddk; a.dk_bs = dk_bs;
+  a.lddv = lddv; a.dv_bs = dv_bs;
+  a.scale = scale;
+  const size_t smem = (size_t)4 * kSA_MAX * kSA_LD * 2 + (size_t)2 * kSA_MAX * kSA_PLD * 4 + 2 * kSA_MAX * 4;
+  static bool attr = false;
+  if (!attr) {
+    E4T_CUDA(cudaFuncSetAttribute(attn_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  attn_small_bwd_kernel<<<dim3(H, B), 256, smem, (cudaStream_t)stream_>>>(a);
+  E4T_COUNT_LAUNCH();
+  E4T_LAUNCH_CHECK();
+  return 0;
+}
