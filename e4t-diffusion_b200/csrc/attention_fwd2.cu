@@ -95,13 +95,16 @@ __device__ __forceinline__ u64 exp2_poly2(u64 x2) {
 }
 
 // POLY8: pairs (of every 8 consecutive pairs) whose exp2 runs on the FMA pipe; 0 = all on MUFU.
-// F16P : P is produced by ex2.approx.f16x2 — ONE MUFU operation per PAIR of scores (measured on B200,
-//        tools/micro/pipe_rates.cu: 0.5 warp-instructions/clk/SM for both the f32 and the f16x2 form, i.e. the packed
-//        form doubles the exponential rate to 32/clk/SM) — and stays fp16: the A operand of O += P V is then fp16 (10
-//        mantissa bits, finer than the bf16 P of the other variants) against a bf16 B operand; fp16's range is ample
-//        because p <= 2^8 with the threshold rescale.  The argument of the exponential is rounded to fp16 first
-//        (|x| < 8 -> absolute error <= 2^-9, i.e. <= 0.14 % on p, the same order as bf16 rounding of p itself).
-template <int POLY8, bool F16P>
+// BF16X: exponentials by ex2.approx.ftz.bf16x2 — ONE MUFU operation per PAIR of scores (measured on B200,
+//        tools/micro/pipe_rates.cu: 0.5 warp-instructions/clk/SM for the f32, f16x2 and bf16x2 forms alike, so the packed
+//        forms double the exponential rate to 32/clk/SM); the result is already the bf16 pair the P·V MMA consumes.
+//        (An fp16 P against a bf16 V is not an option: tcgen05.mma kind::f16 with a_format != b_format raises an
+//        illegal-instruction error on sm_100a — tried in round 2.)  The price is that the ARGUMENT (s - m)·scale·log2e
+//        is rounded to bf16 before the exponential: relative error of p <= 0.00135·|x|, i.e. below the 2^-9 rounding
+//        of p itself for |x| < 1.4 and growing only where p has already decayed by 2^-|x|.
+// The MUFU instructions are `asm volatile`: plain asm let the compiler hoist the whole exponential phase above the
+// exp-phase token barrier (ncu r02: both warpgroups then ran in lock-step and waited 31 % of the time for S).
+template <int POLY8, bool BF16X>
 __global__ void __launch_bounds__(384, 1)
 attn_fwd2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                  const __grid_constant__ CUtensorMap mapV, const AttnArgs a) {
@@ -122,6 +125,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
   uint64_t* p_ready = s_full + 2;     // [2]  softmax t -> MMA : P_t(j) written, O_t rescaled
   uint64_t* o_done = p_ready + 2;     // [2]  MMA -> softmax t : last P_t V retired
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+  float* s_zero = reinterpret_cast<float*>(tmem_slot + 2);   // 0.0f: read after the exp-phase token (ordering anchor)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 256, h = blockIdx.y, b = blockIdx.z;
@@ -139,6 +143,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
       mbar_init(&p_ready[i], 128);
       mbar_init(&o_done[i], 1);
     }
+    *s_zero = 0.f;
     fence_mbar_init();
   }
   if (warp == 0 && lane == 0) {
@@ -179,8 +184,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     const uint32_t idesc_s = umma_idesc_bf16(128u, false, false);
-    // O += P V: A = P from TMEM (bf16, or fp16 when F16P: a_format field, bits 7-9, = 0), B = V (bf16, MN-major)
-    const uint32_t idesc_o = umma_idesc_bf16((uint32_t)a.dpad, false, true) & (F16P ? ~(7u << 7) : ~0u);
+    const uint32_t idesc_o = umma_idesc_bf16((uint32_t)a.dpad, false, true);
     mbar_wait(q_full, 0);
     mbar_wait(&k_full[0], 0);
     tc_fence_after();
@@ -272,45 +276,82 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
           }
         }
       }
-      const float nmb = -m * sl2;
-      const u64 nmb2 = f2_pack(nmb, nmb);
+      float nmb = -m * sl2;
       // exp-phase token: the two softmax warpgroups take turns on the MUFU pipe, so that the tensor-core work of tile t
       // (P_t V, then S_t of the next block) always runs under the exponentials of tile 1-t instead of both
-      // warpgroups finishing together and then both waiting for the tensor core
+      // warpgroups finishing together and then both waiting for the tensor core.  ptxas is free to move pure
+      // register arithmetic across a bar.sync, so the whole exponential phase is made to depend on a (zero) value
+      // loaded from shared memory AFTER the barrier.
       if (a.pbuf) {
         if (t == 0) asm volatile("bar.sync 2, 256;" ::: "memory");
         else asm volatile("bar.sync 3, 256;" ::: "memory");
+        float z;
+        asm volatile("ld.volatile.shared.f32 %0, [%1];" : "=f"(z) : "r"(smem_u32(s_zero)) : "memory");
+        nmb += z;
       }
+      const u64 nmb2 = f2_pack(nmb, nmb);
       u64 ls = f2_pack(0.f, 0.f), ls2 = f2_pack(0.f, 0.f);
+      // Software-pipelined by hand (the SM issues in order): the MUFU results of pair e are consumed (row sum, bf16
+      // pack) kLag pairs later, and the scale-and-subtract FFMA2 of pair e + kLead is issued in between, so that no
+      // instruction waits on the ~20-clk MUFU latency of the instruction just before it.  (ncu r02: with
+      // produce-then-consume order the exponential phase of one warp took 1670 clk against 1024 clk of MUFU time.)
+      constexpr int kLag = 6, kLead = 4;
+      if constexpr (BF16X || POLY8 != 0) {
 #pragma unroll
-      for (int e = 0; e < 64; ++e) {               // pair e = columns 2e, 2e+1
-        const u64 x2 = f2_fma(f2_pack(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1])), sl2_2, nmb2);
-        u64 p2;
-        if constexpr (F16P) {
-          float x0, x1;
-          f2_unpack(x2, x0, x1);
-          uint32_t hx, he;
-          asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hx) : "f"(x1), "f"(x0));
-          asm("ex2.approx.f16x2 %0, %1;" : "=r"(he) : "r"(hx));
-          float p0, p1;
-          asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tcvt.f32.f16 %0, lo;\n\tcvt.f32.f16 %1, hi;\n\t}"
-              : "=f"(p0), "=f"(p1) : "r"(he));
-          p2 = f2_pack(p0, p1);
-          v[e] = he;
-        } else {
-          if ((e & 7) < POLY8) {
-            p2 = exp2_poly2(x2);
-          } else {
+        for (int e = 0; e < 64; ++e) {               // pair e = columns 2e, 2e+1 (variants kept for measurements)
+          const u64 x2 = f2_fma(f2_pack(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1])), sl2_2, nmb2);
+          u64 p2;
+          if constexpr (BF16X) {
             float x0, x1;
             f2_unpack(x2, x0, x1);
-            p2 = f2_pack(ex2_approx(x0), ex2_approx(x1));
+            uint32_t hx, he;
+            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hx) : "f"(x1), "f"(x0));
+            asm volatile("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(he) : "r"(hx));
+            p2 = f2_pack(__uint_as_float(he << 16), __uint_as_float(he & 0xffff0000u));
+            v[e] = he;
+          } else {
+            if ((e & 7) < POLY8) {
+              p2 = exp2_poly2(x2);
+            } else {
+              float x0, x1, p0, p1;
+              f2_unpack(x2, x0, x1);
+              asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(x0));
+              asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(x1));
+              p2 = f2_pack(p0, p1);
+            }
+            float p0, p1;
+            f2_unpack(p2, p0, p1);
+            v[e] = pack_bf16(p0, p1);
           }
-          float p0, p1;
-          f2_unpack(p2, p0, p1);
-          v[e] = pack_bf16(p0, p1);
+          if (e & 1) ls2 = f2_add(ls2, p2);
+          else ls = f2_add(ls, p2);
         }
-        if (e & 1) ls2 = f2_add(ls2, p2);
-        else ls = f2_add(ls, p2);
+      } else {
+        u64 xq[64];                                  // x of pair e, then p of pair e (registers of v[] are recycled)
+#pragma unroll
+        for (int e = 0; e < kLead; ++e)
+          xq[e] = f2_fma(f2_pack(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1])), sl2_2, nmb2);
+#pragma unroll
+        for (int e = 0; e < 64 + kLag; ++e) {
+          if (e < 64) {
+            float x0, x1, p0, p1;
+            f2_unpack(xq[e], x0, x1);
+            asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(x0));
+            if (e + kLead < 64)
+              xq[e + kLead] = f2_fma(f2_pack(__uint_as_float(v[2 * (e + kLead)]), __uint_as_float(v[2 * (e + kLead) + 1])),
+                                     sl2_2, nmb2);
+            asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(x1));
+            xq[e] = f2_pack(p0, p1);
+          }
+          if (e >= kLag) {
+            const int c = e - kLag;
+            if (c & 1) ls2 = f2_add(ls2, xq[c]);
+            else ls = f2_add(ls, xq[c]);
+            float p0, p1;
+            f2_unpack(xq[c], p0, p1);
+            v[c] = pack_bf16(p0, p1);
+          }
+        }
       }
       if (a.pbuf && !(t == 1 && j == a.nblk - 1)) {   // hand the token to the other warpgroup
         if (t == 0) asm volatile("bar.arrive 3, 256;" ::: "memory");
@@ -375,14 +416,14 @@ int e4t_attn_fwd2_try(const void* Q, const void* K, const void* V, void* O, floa
                       long long ldq, long long q_bs, long long ldk, long long k_bs, long long ldv, long long v_bs,
                       long long ldo, long long o_bs, float scale, cudaStream_t st) {
   // E4T_ATTN_FWD2: "0" disables this kernel; otherwise a string of flags: 'p<k>' FMA-pipe exp2 for k of every 8 pairs,
-  // 'h' fp16 P through ex2.approx.f16x2, 'n' no exp-phase token (both warpgroups free-running)
+  // 'b' exponentials by ex2.approx.ftz.bf16x2, 'n' no exp-phase token (both warpgroups free-running)
   const char* e = getenv("E4T_ATTN_FWD2");
   int poly8 = 0, f16p = 0, token = 1;
   if (e) {
     if (e[0] == '0' && e[1] == 0) return 0;
     for (const char* c = e; *c; ++c) {
       if (*c == 'p' && c[1] >= '0' && c[1] <= '7') poly8 = c[1] - '0';
-      if (*c == 'h') f16p = 1;
+      if (*c == 'b') f16p = 1;
       if (*c == 'n') token = 0;
     }
   }

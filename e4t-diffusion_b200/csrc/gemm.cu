@@ -20,7 +20,7 @@ struct GemmArgs {
   int M, N, K, batch;
   int BN, m_tiles, n_tiles, splits, kchunks, kper, stages;
   int a_mn, b_mn, a_batched, b_batched;
-  // implicit 3x3 convolution
+  // implicit 3x3 convolution (conv = 1: forward / dgrad, 2: weight gradient)
   int conv, H, W, BH, BB, cin_chunks, cout;
   // epilogue
   void* out;
@@ -101,7 +101,7 @@ e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         const int kc0 = sp * g.kper;
         const int kc1 = min(g.kchunks, kc0 + g.kper);
         int cb0 = 0, ch0 = 0;
-        if (g.conv) {
+        if (g.conv == 1) {
           const int img = g.H * g.W;
           cb0 = m0 / img;
           ch0 = (m0 % img) / g.W;
@@ -112,7 +112,18 @@ e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
           uint8_t* sB = sA + kATileBytes;
           if (elect_one()) {
           mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
-          if (g.conv) {
+          if (g.conv == 2) {
+            // 3x3 weight gradient: dW[tap][co][ci] = sum_p dY[p][co] * X[p + tap][ci].  A = dY (MN-major, 64 pixels of
+            // K per chunk), B = the tap-shifted input pixels (MN-major; same 4-D box + out-of-bounds zero fill as the
+            // forward's A operand, 64 pixels x 64 channels per N chunk); batch index = tap
+            const int tap = bz, dy = tap / 3, dx = tap % 3;
+            const int p0 = kc * kBK, img = g.H * g.W;
+            const int b0 = p0 / img, h0 = (p0 % img) / g.W;
+            tma_load_3d(sA, &mapA, &full_bar[s], m0, p0, 0);
+            tma_load_3d(sA + 8192, &mapA, &full_bar[s], m0 + 64, p0, 0);
+            for (int i = 0; i < g.BN / 64; ++i)
+              tma_load_4d(sB + i * 8192, &mapB, &full_bar[s], n0 + 64 * i, dx - 1, h0 + dy - 1, b0);
+          } else if (g.conv) {
             const int tap = kc / g.cin_chunks, cc = kc % g.cin_chunks;
             const int dy = tap / 3, dx = tap % 3;
             tma_load_4d(sA, &mapA, &full_bar[s], cc * kBK, dx - 1, ch0 + dy - 1, cb0);
@@ -613,6 +624,51 @@ extern "C" int e4t_conv3x3_bf16(const void* x, const void* w, void* out, int B, 
     uint64_t str[1] = {(uint64_t)Cin * 2};
     uint32_t box[2] = {kBK, (uint32_t)g.BN};
     if (int e = e4t_tmap_encode(&mB, w, 2, dims, str, box, 2)) return e;
+  }
+  return launch_gemm(mA, mB, g, stream);
+}
+
+// 3x3 / stride 1 / pad 1 weight gradient: dw9[tap][co][ci] += sum_{b,y,x} dy[b][y][x][co] * x[b][y+ky-1][x+kx-1][ci]
+// (tap = ky*3+kx; fp32 atomic accumulation, split-K over the pixels).  x NHWC bf16 [B][H][W][Cin], dy [B][H][W][Cout].
+// Replaces autograd's conv2d weight gradient behind every ResnetBlock2D / Upsample2D / Downsample2D conv when the base
+// UNet is trainable (tuning_e4t.py:139-146).  Cin, Cout % 64 == 0; W | 64; H*W % 64 == 0.
+extern "C" int e4t_conv3x3_wgrad(const void* x, const void* dy, float* dw9, int B, int H, int W, int Cin, int Cout,
+                                 void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  E4T_CHECK(Cin % 64 == 0 && Cout % 64 == 0, "e4t_conv3x3_wgrad: Cin, Cout must be multiples of 64 (%d, %d)", Cin, Cout);
+  E4T_CHECK(W <= 64 && (64 % W) == 0 && (H * W) % 64 == 0 && H % (64 / W) == 0,
+            "e4t_conv3x3_wgrad: unsupported image %dx%d (W | 64, H*W %% 64 == 0)", H, W);
+  const long long pixels = (long long)B * H * W;
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.M = Cout; g.N = Cin; g.K = (int)pixels; g.batch = 9;
+  g.a_mn = 1; g.b_mn = 1; g.a_batched = 0; g.b_batched = 1;
+  g.conv = 2; g.H = H; g.W = W; g.cout = Cout;
+  g.m_tiles = cdiv(Cout, kBM);
+  g.kchunks = (int)(pixels / kBK);
+  // enough K-splits to fill the machine about twice: tiles = 9 taps x m_tiles x n_tiles x splits
+  const int base_tiles = 9 * g.m_tiles * cdiv(Cin, 256);
+  int splits = cdiv(2 * num_sms(), base_tiles);
+  if (splits < 1) splits = 1;
+  if (splits > g.kchunks) splits = g.kchunks;
+  g.kper = cdiv(g.kchunks, splits);
+  g.splits = cdiv(g.kchunks, g.kper);
+  g.BN = Cin >= 256 ? 256 : (Cin >= 192 ? 192 : (Cin >= 128 ? 128 : 64));
+  g.n_tiles = cdiv(Cin, g.BN);
+  g.out = dw9; g.out_mode = 2; g.ldo = Cin; g.out_bstride = (long long)Cout * Cin;
+  g.rows_per_group = 1; g.alpha = 1.f;
+  CUtensorMap mA, mB;
+  {
+    uint64_t dims[3] = {(uint64_t)Cout, (uint64_t)pixels, 1};
+    uint64_t str[2] = {(uint64_t)Cout * 2, (uint64_t)pixels * Cout * 2};
+    uint32_t box[3] = {64, kBK, 1};
+    if (int e = e4t_tmap_encode(&mA, dy, 3, dims, str, box, 2)) return e;
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)H * W * Cin * 2};
+    uint32_t box[4] = {64, (uint32_t)W, (uint32_t)(64 / W), 1};
+    if (int e = e4t_tmap_encode(&mB, x, 4, dims, str, box, 2)) return e;
   }
   return launch_gemm(mA, mB, g, stream);
 }

@@ -83,13 +83,16 @@ extern "C" int e4t_act_bwd(const void* x, const void* dy, void* dx, long long n,
 // block = 32 x 8 threads: each thread owns 8 consecutive columns (one 16-byte load), the 8 thread-rows stride over m
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ X, float* __restrict__ out, long long M,
-                                                     int N, long long ld, int rows_per_block) {
+                                                     int N, long long ld, int rows_per_block, int blocks_per_group,
+                                                     long long rows_per_group) {
   __shared__ float red[8][256 + 8];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int n0 = (blockIdx.x * 32 + tx) * 8;
-  const long long m0 = (long long)blockIdx.y * rows_per_block;
+  const long long grp = blockIdx.y / blocks_per_group;
+  const long long m0 = grp * rows_per_group + (long long)(blockIdx.y % blocks_per_group) * rows_per_block;
   long long m1 = m0 + rows_per_block;
-  if (m1 > M) m1 = M;
+  const long long gend = (grp + 1) * rows_per_group < M ? (grp + 1) * rows_per_group : M;
+  if (m1 > gend) m1 = gend;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (n0 < N) {
     for (long long m = m0 + ty; m < m1; m += 8) {
@@ -107,17 +110,210 @@ __global__ void __launch_bounds__(256) colsum_kernel(const bf16* __restrict__ X,
 #pragma unroll
   for (int r = 0; r < 8; ++r) s += red[r][c];
   const int n = blockIdx.x * 256 + c;
-  if (n < N) atomicAdd(out + n, s);
+  if (n < N) atomicAdd(out + grp * N + n, s);
 }
-extern "C" int e4t_colsum_acc(const void* X, float* out, long long M, int N, long long ld, void* stream_) {
+// out[g][n] += sum over the rows m of group g (m / rows_per_group == g) of X[m][n]; rows_per_group <= 0: one group.
+// Bias gradients (one group) and the per-image time-embedding row gradient of ResnetBlock2D (group = image).
+extern "C" int e4t_colsum_acc(const void* X, float* out, long long M, int N, long long ld, long long rows_per_group,
+                              void* stream_) {
   E4T_CHECK(N % 8 == 0 && ld % 8 == 0, "e4t_colsum_acc: N and ld must be multiples of 8");
   if (M <= 0) return 0;
+  if (rows_per_group <= 0 || rows_per_group > M) rows_per_group = M;
+  E4T_CHECK(M % rows_per_group == 0, "e4t_colsum_acc: M must be a multiple of rows_per_group");
+  const long long groups = M / rows_per_group;
   const int gx = cdiv(N, 256);
-  long long gy = (148 * 4 + gx - 1) / gx;
-  int rpb = (int)((M + gy - 1) / gy);
+  long long bpg = (148 * 4 + gx * groups - 1) / (gx * groups);
+  if (bpg < 1) bpg = 1;
+  int rpb = (int)((rows_per_group + bpg - 1) / bpg);
   if (rpb < 64) rpb = 64;
-  gy = (M + rpb - 1) / rpb;
-  colsum_kernel<<<dim3(gx, (unsigned)gy), 256, 0, (cudaStream_t)stream_>>>((const bf16*)X, out, M, N, ld, rpb);
+  bpg = (rows_per_group + rpb - 1) / rpb;
+  colsum_kernel<<<dim3(gx, (unsigned)(groups * bpg)), 256, 0, (cudaStream_t)stream_>>>((const bf16*)X, out, M, N, ld, rpb,
+                                                                                     (int)bpg, rows_per_group);
+  E4T_COUNT_LAUNCH();
+  E4T_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// affine-parameter gradients of LayerNorm / GroupNorm(+SiLU):  dgamma[c] += sum_r dz[r][c] * xhat[r][c],
+// dbeta[c] += sum_r dz[r][c], with xhat = (x - mean) * rstd and dz = dy (LayerNorm, GroupNorm) or dy * silu'(z),
+// z = xhat * gamma + beta (GroupNorm+SiLU).  Statistics:
+//   PERCOL = false (LayerNorm): stats fp32 [rows][2] = (mean, rstd) per row
+//   PERCOL = true  (GroupNorm): mean_c / rstd_c fp32 [rows / rows_per_group][C] per (image, channel)
+// ---------------------------------------------------------------------------------------------
+template <bool PERCOL>
+__global__ void __launch_bounds__(256) norm_param_grad_kernel(const bf16* __restrict__ X, const bf16* __restrict__ dY,
+                                                              const float* __restrict__ st0, const float* __restrict__ st1,
+                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                              float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                              long long rows, int C, int rows_per_block,
+                                                              long long rows_per_group, int silu) {
+  __shared__ float red[2][8][256 + 8];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n0 = (blockIdx.x * 32 + tx) * 8;
+  const long long m0 = (long long)blockIdx.y * rows_per_block;
+  long long m1 = m0 + rows_per_block;
+  if (m1 > rows) m1 = rows;
+  float ag[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ab[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (n0 < C) {
+    float gm[8], bt[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      gm[j] = gamma[n0 + j];
+      bt[j] = beta ? beta[n0 + j] : 0.f;
+    }
+    for (long long m = m0 + ty; m < m1; m += 8) {
+      const uint4 ux = *reinterpret_cast<const uint4*>(X + m * C + n0);
+      const uint4 ud = *reinterpret_cast<const uint4*>(dY + m * C + n0);
+      const uint32_t xs[4] = {ux.x, ux.y, ux.z, ux.w}, ds[4] = {ud.x, ud.y, ud.z, ud.w};
+      float mean[8], rstd[8];
+      if (PERCOL) {
+        const long long g = m / rows_per_group;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          mean[j] = st0[g * C + n0 + j];
+          rstd[j] = st1[g * C + n0 + j];
+        }
+      } else {
+        const float mu = st0[m * 2], rs = st0[m * 2 + 1];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          mean[j] = mu;
+          rstd[j] = rs;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 xv = unpack_bf16(xs[q]), dv = unpack_bf16(ds[q]);
+        const float xin[2] = {xv.x, xv.y}, din[2] = {dv.x, dv.y};
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int j = 2 * q + u;
+          const float xh = (xin[u] - mean[j]) * rstd[j];
+          float dz = din[u];
+          if (silu) {
+            const float z = xh * gm[j] + bt[j];
+            const float sg = 1.f / (1.f + __expf(-z));
+            dz *= sg * (1.f + z * (1.f - sg));
+          }
+          ag[j] += dz * xh;
+          ab[j] += dz;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    red[0][ty][tx * 8 + j] = ag[j];
+    red[1][ty][tx * 8 + j] = ab[j];
+  }
+  __syncthreads();
+  const int c = threadIdx.x;
+  float sg = 0.f, sb = 0.f;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    sg += red[0][r][c];
+    sb += red[1][r][c];
+  }
+  const int n = blockIdx.x * 256 + c;
+  if (n < C) {
+    atomicAdd(dgamma + n, sg);
+    atomicAdd(dbeta + n, sb);
+  }
+}
+static void norm_grid(long long rows, int C, int& gx, long long& gy, int& rpb) {
+  gx = cdiv(C, 256);
+  gy = (148 * 4 + gx - 1) / gx;
+  rpb = (int)((rows + gy - 1) / gy);
+  if (rpb < 64) rpb = 64;
+  gy = (rows + rpb - 1) / rpb;
+}
+// LayerNorm: x, dy bf16 [rows][C]; stats fp32 [rows][2] (mean, rstd) as written by e4t_layernorm_fwd.
+extern "C" int e4t_layernorm_param_grad(const void* x, const void* dy, const float* stats, const float* gamma,
+                                        float* dgamma, float* dbeta, long long rows, int C, void* stream_) {
+  E4T_CHECK(C % 8 == 0, "e4t_layernorm_param_grad: C %% 8 != 0");
+  if (rows <= 0) return 0;
+  int gx, rpb; long long gy;
+  norm_grid(rows, C, gx, gy, rpb);
+  norm_param_grad_kernel<false><<<dim3(gx, (unsigned)gy), 256, 0, (cudaStream_t)stream_>>>(
+      (const bf16*)x, (const bf16*)dy, stats, nullptr, gamma, nullptr, dgamma, dbeta, rows, C, rpb, 1, 0);
+  E4T_COUNT_LAUNCH();
+  E4T_LAUNCH_CHECK();
+  return 0;
+}
+// GroupNorm(+SiLU): x, dy bf16 [B*HW][C]; mean_c / rstd_c fp32 [B][C] (group statistics expanded per channel).
+extern "C" int e4t_groupnorm_param_grad(const void* x, const void* dy, const float* mean_c, const float* rstd_c,
+                                        const float* gamma, const float* beta, float* dgamma, float* dbeta, int B, int HW,
+                                        int C, int act_silu, void* stream_) {
+  E4T_CHECK(C % 8 == 0, "e4t_groupnorm_param_grad: C %% 8 != 0");
+  const long long rows = (long long)B * HW;
+  if (rows <= 0) return 0;
+  int gx, rpb; long long gy;
+  norm_grid(rows, C, gx, gy, rpb);
+  norm_param_grad_kernel<true><<<dim3(gx, (unsigned)gy), 256, 0, (cudaStream_t)stream_>>>(
+      (const bf16*)x, (const bf16*)dy, mean_c, rstd_c, gamma, beta, dgamma, dbeta, rows, C, rpb, HW, act_silu);
+  E4T_COUNT_LAUNCH();
+  E4T_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// weight gradients of the UNet's two narrow convolutions (conv_in 4 -> C, conv_out C -> 4; 3x3, pad 1):
+//   acc[w][n][tap] += sum_{b,y,x} wide[b][y][x][w] * narrow[b][n][y + sgn*(ky-1)][x + sgn*(kx-1)]
+// wide: bf16 NHWC [B][H][W][Cw]; narrow: fp32 NCHW [B][Cn][H][W] (Cn <= 4); acc fp32 [Cw][Cn][9].
+//   conv_in  (unet_2d_condition.py:481): wide = dY, narrow = latent input, sgn = +1 -> acc = dW[co][ci][ky][kx]
+//   conv_out (unet_2d_condition.py:557): wide = X,  narrow = dY,           sgn = -1 -> acc[ci][co][tap] = dW[co][ci][ky][kx]
+// one thread per wide channel, 36 register accumulators; a block walks `rows_per_block` image rows.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(320) narrow_conv_wgrad_kernel(const bf16* __restrict__ wide,
+                                                                const float* __restrict__ narrow, float* __restrict__ acc,
+                                                                int H, int W, int Cw, int Cn, int sgn, int rows_per_block) {
+  extern __shared__ float patch[];   // [Cn][rows_per_block + 2][W + 2]
+  const int b = blockIdx.z, y0 = blockIdx.y * rows_per_block;
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  const int PW = W + 2, PH = rows_per_block + 2;
+  for (int i = threadIdx.x; i < Cn * PH * PW; i += blockDim.x) {
+    const int n = i / (PH * PW), r = (i / PW) % PH, c = i % PW;
+    const int y = y0 + r - 1, x = c - 1;
+    patch[i] = (y >= 0 && y < H && x >= 0 && x < W) ? narrow[(((long long)b * Cn + n) * H + y) * W + x] : 0.f;
+  }
+  __syncthreads();
+  if (w >= Cw) return;
+  float a[4][9];
+#pragma unroll
+  for (int n = 0; n < 4; ++n)
+#pragma unroll
+    for (int t = 0; t < 9; ++t) a[n][t] = 0.f;
+  for (int r = 0; r < rows_per_block && y0 + r < H; ++r) {
+    for (int x = 0; x < W; ++x) {
+      const float v = __bfloat162float(wide[(((long long)b * H + y0 + r) * W + x) * Cw + w]);
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        if (n < Cn) {
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            const int dy = sgn * (t / 3 - 1), dx = sgn * (t % 3 - 1);
+            a[n][t] += v * patch[(n * PH + r + 1 + dy) * PW + x + 1 + dx];
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int n = 0; n < 4; ++n)
+    if (n < Cn)
+#pragma unroll
+      for (int t = 0; t < 9; ++t) atomicAdd(acc + ((long long)w * Cn + n) * 9 + t, a[n][t]);
+}
+extern "C" int e4t_narrow_conv_wgrad(const void* wide, const float* narrow, float* acc, int B, int H, int W, int Cw,
+                                     int Cn, int sgn, void* stream_) {
+  E4T_CHECK(Cn >= 1 && Cn <= 4, "e4t_narrow_conv_wgrad: narrow channel count must be 1..4 (got %d)", Cn);
+  E4T_CHECK(sgn == 1 || sgn == -1, "e4t_narrow_conv_wgrad: sgn must be +-1");
+  const int rpb = H >= 8 ? 8 : H;
+  const size_t smem = (size_t)Cn * (rpb + 2) * (W + 2) * sizeof(float);
+  const int threads = Cw >= 320 ? 320 : ((Cw + 31) / 32 * 32);
+  narrow_conv_wgrad_kernel<<<dim3(cdiv(Cw, threads), cdiv(H, rpb), B), threads, smem, (cudaStream_t)stream_>>>(
+      (const bf16*)wide, narrow, acc, H, W, Cw, Cn, sgn, rpb);
   E4T_COUNT_LAUNCH();
   E4T_LAUNCH_CHECK();
   return 0;

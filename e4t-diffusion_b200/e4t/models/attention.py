@@ -18,7 +18,7 @@ class GEGLU(nn.Module):
         self.proj = nn.Linear(dim_in, dim_out * 2)
 
     def forward(self, hidden_states):
-        h = FN.LinearFn.apply(hidden_states, _weight_bf16(self.proj), self.proj.bias, None)
+        h = FN.LinearFn.apply(hidden_states, _weight_bf16(self.proj), self.proj.bias, None, self.proj.weight)
         return FN.GEGLUFn.apply(h)
 
 
@@ -36,7 +36,7 @@ class FeedForward(nn.Module):
 
     def forward(self, hidden_states, residual=None):
         h = self.net[0](hidden_states)
-        return FN.LinearFn.apply(h, _weight_bf16(self.net[2]), self.net[2].bias, residual)
+        return FN.LinearFn.apply(h, _weight_bf16(self.net[2]), self.net[2].bias, residual, self.net[2].weight)
 
 
 class BasicTransformerBlock(nn.Module):

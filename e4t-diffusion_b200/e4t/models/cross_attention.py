@@ -57,7 +57,7 @@ class CrossAttention(nn.Module):
             w_eff, dweff, token = bank.get(self, group)
             if token is not None:
                 return FN.WOLinearBankFn.apply(x, w_eff, dweff, token)
-            return FN.LinearFn.apply(x, w_eff, None, None)
+            return FN.LinearFn.apply(x, w_eff, None, None, None)
         w_eff, carrier = self.effective_weights(group)
         return FN.WOLinearFn.apply(x, w_eff, carrier)
 
@@ -162,7 +162,7 @@ class B200AttnProcessor:
             kv = attn._project(ctx, "kv")
             o = FN.AttentionFn.apply(q, kv, attn.heads, attn.scale)
         out = attn.to_out[0]
-        y = FN.LinearFn.apply(o, _weight_bf16(out), out.bias, residual)
+        y = FN.LinearFn.apply(o, _weight_bf16(out), out.bias, residual, out.weight)
         if attn.to_out[1].p > 0.0 and attn.training:
             y = attn.to_out[1](y)
         return y

@@ -23,7 +23,7 @@ def conv_w9_dgrad(conv):
 
 
 def conv3x3(conv, x, rowgroup=None, residual=None):
-    return FN.Conv3x3Fn.apply(x, conv_w9(conv), conv_w9_dgrad(conv), conv.bias, rowgroup, residual)
+    return FN.Conv3x3Fn.apply(x, conv_w9(conv), conv_w9_dgrad(conv), conv.bias, rowgroup, residual, conv.weight)
 
 
 class Upsample2D(nn.Module):
@@ -101,7 +101,8 @@ class ResnetBlock2D(nn.Module):
             return None
         if self._temb_row is not None and self._temb_row[0] is temb:
             return self._temb_row[1]
-        with torch.no_grad():
+        # stand-alone use (no UNet-level batched projection): differentiable when the projection is trainable
+        with torch.set_grad_enabled(torch.is_grad_enabled() and self.time_emb_proj.weight.requires_grad):
             return F.linear(F.silu(temb.float()), self.time_emb_proj.weight, self.time_emb_proj.bias).contiguous()
 
     def forward(self, input_tensor, temb):
@@ -116,5 +117,6 @@ class ResnetBlock2D(nn.Module):
             B, H, W, C = x.shape
             w = FN.prepared(self.conv_shortcut.weight, "bf16_1x1",
                             lambda t: t.reshape(t.shape[0], t.shape[1]).to(torch.bfloat16).contiguous())
-            x = FN.LinearFn.apply(x.view(B, H * W, C), w, self.conv_shortcut.bias, None).view(B, H, W, -1)
+            x = FN.LinearFn.apply(x.view(B, H * W, C), w, self.conv_shortcut.bias, None,
+                                  self.conv_shortcut.weight).view(B, H, W, -1)
         return conv3x3(self.conv2, h, residual=x)

@@ -70,11 +70,13 @@ class Transformer2DModel(ModelMixin, ConfigMixin):
         x = hidden_states
         B, H, W, C = x.shape
         h = FN.GroupNormFn.apply(x, self.norm.weight, self.norm.bias, self.norm.num_groups, self.norm.eps, False)
-        h = FN.LinearFn.apply(h.view(B, H * W, C), self._w(self.proj_in), self.proj_in.bias, None)      # :253-261
+        h = FN.LinearFn.apply(h.view(B, H * W, C), self._w(self.proj_in), self.proj_in.bias, None,
+                              self.proj_in.weight)                                                   # :253-261
         for block in self.transformer_blocks:                                                           # :268-275
             h = block(h, encoder_hidden_states=encoder_hidden_states, timestep=timestep,
                       cross_attention_kwargs=cross_attention_kwargs, class_labels=class_labels)
-        out = FN.LinearFn.apply(h, self._w(self.proj_out), self.proj_out.bias, x.view(B, H * W, C))      # :279-286
+        out = FN.LinearFn.apply(h, self._w(self.proj_out), self.proj_out.bias, x.view(B, H * W, C),
+                                self.proj_out.weight)                                                # :279-286
         out = out.view(B, H, W, C)
         if not return_dict:
             return (out,)

@@ -197,11 +197,28 @@ class UNet2DConditionModel(ModelMixin, ConfigMixin):
         elif len(timesteps.shape) == 0:
             timesteps = timesteps[None].to(device)
         timesteps = timesteps.to(device).expand(batch)
+        resnets = self._resnets()
+        trainable = torch.is_grad_enabled() and (any(p.requires_grad for p in self.time_embedding.parameters())
+                                                 or any(r.time_emb_proj.weight.requires_grad for r in resnets))
+        if trainable:
+            # tuning_e4t.py trains the whole UNet: the time-embedding MLP and the 22 per-block projections stay on
+            # differentiable fp32 torch ops (a (B,320)->(B,1280)->(B,ΣCout) chain, negligible FLOPs); their gradients
+            # arrive through the row-add operand of each block's first convolution (Conv3x3Fn returns d(row add))
+            t_emb = self.time_proj(timesteps).to(torch.float32)
+            emb = self.time_embedding(t_emb)
+            w_cat = torch.cat([r.time_emb_proj.weight for r in resnets], dim=0)
+            b_cat = torch.cat([r.time_emb_proj.bias for r in resnets], dim=0)
+            rows = F.linear(F.silu(emb), w_cat, b_cat)
+            off = 0
+            for r in resnets:
+                c = r.time_emb_proj.out_features
+                r._temb_row = (emb, rows[:, off:off + c].contiguous())
+                off += c
+            return emb
         with torch.no_grad():
             t_emb = self.time_proj(timesteps).to(torch.float32)
             emb = self.time_embedding(t_emb)                                       # unet_2d_condition.py:461-468
             # all ResnetBlock2D time_emb_proj(silu(emb)) projections in ONE fp32 matmul
-            resnets = self._resnets()
             ws = [r.time_emb_proj.weight for r in resnets]
             key = tuple((w._version, w.data_ptr()) for w in ws)
             cache = getattr(self, "_temb_cat", None)
@@ -236,9 +253,7 @@ class UNet2DConditionModel(ModelMixin, ConfigMixin):
         B = sample.shape[0]
         emb = self._time_embed(timestep, B, sample.device)
         ehs = FN.as_bf16(encoder_hidden_states).contiguous()
-        with torch.no_grad():
-            x = ops.conv_in_fwd(sample.detach().float().contiguous(), self.conv_in.weight.detach(),
-                                self.conv_in.bias.detach())                        # :481 (input has no grad)
+        x = FN.ConvInFn.apply(sample, self.conv_in.weight, self.conv_in.bias)       # :481 (the latent input has no grad)
         res = (x,)
         for blk in self.down_blocks:                                               # :485-496
             if getattr(blk, "has_cross_attention", False):

@@ -130,12 +130,15 @@ class FlatAdamW:
                 setattr(self, k, tuple(sd[k]) if k == "betas" else sd[k])
 
 
-def trainable_parameters(unet, e4t_encoder):
-    """optim_params of pretrain_e4t.py:274-278: encoder params with requires_grad + UNet params whose name has 'wo'."""
+def trainable_parameters(unet, e4t_encoder, tune_unet=False):
+    """Pre-training (pretrain_e4t.py:274-278): encoder params with requires_grad + UNet params whose name has 'wo'.
+    The reference leaves every base UNet weight at requires_grad=True, computes (and all-reduces) their gradients and
+    never applies them; here they are frozen, which changes no result and lets the kernels skip ~0.8 TFLOP/img of
+    weight-gradient work.  Domain tuning (tuning_e4t.py:139-146, tune_unet=True): encoder params + ALL UNet params."""
     ps = [p for p in e4t_encoder.parameters() if p.requires_grad]
     for n, p in unet.named_parameters():
-        if "wo" in n:
-            p.requires_grad = True
+        p.requires_grad_(bool(tune_unet) or "wo" in n)
+        if p.requires_grad:
             ps.append(p)
     return ps
 
@@ -145,7 +148,8 @@ class PretrainStep:
 
     def __init__(self, unet, e4t_encoder, text_encoder, placeholder_token_id, class_token_id, lr=1.6e-5,
                  betas=(0.9, 0.999), weight_decay=1e-2, eps=1e-8, domain_embed_scale=0.1, reg_lambda=0.01,
-                 bos_id=49406, eos_id=49407, weight_dtype=torch.bfloat16, optimizer=True):
+                 bos_id=49406, eos_id=49407, weight_dtype=torch.bfloat16, optimizer=True, tune_unet=False,
+                 max_grad_norm=None):
         self.unet, self.enc, self.text = unet, e4t_encoder, text_encoder
         self.placeholder_token_id = placeholder_token_id
         self.domain_embed_scale, self.reg_lambda = domain_embed_scale, reg_lambda
@@ -158,8 +162,11 @@ class PretrainStep:
             self.class_embed = emb(torch.tensor([class_token_id], device=dev)).float()   # :561-564  (1,768)
             ids = torch.tensor([[bos_id] + [eos_id] * 76], device=dev)
             self.ehs_e4t = self.text(input_ids=ids)[0].to(weight_dtype)                  # :565-583  (1,77,768)
-        self.opt = FlatAdamW(trainable_parameters(unet, e4t_encoder), lr=lr, betas=betas, weight_decay=weight_decay,
-                             eps=eps) if optimizer else None
+        # tune_unet / max_grad_norm: the domain-tuning step (tuning_e4t.py:270-338): every UNet weight trainable,
+        # global gradient-norm clipping over UNet + encoder parameters (:329-335)
+        self.tune_unet, self.max_grad_norm = tune_unet, max_grad_norm
+        self.opt = FlatAdamW(trainable_parameters(unet, e4t_encoder, tune_unet), lr=lr, betas=betas,
+                             weight_decay=weight_decay, eps=eps) if optimizer else None
         self._graph = None
         self.wo_bank = None
         if self.opt is not None:
@@ -264,6 +271,11 @@ class PretrainStep:
     def _apply_optimizer(self):
         if self.opt is not None:
             scale = self.opt.all_reduce_grads()
+            if self.max_grad_norm is not None:
+                # accelerator.clip_grad_norm_ (tuning_e4t.py:329-335) == torch clip_grad_norm_: one norm over the flat
+                # gradient arena (its padding is zero), coefficient kept on the device (graph-replayable)
+                total = torch.linalg.vector_norm(self.opt.grad) * scale
+                self.opt.grad.mul_(torch.clamp(self.max_grad_norm / (total + 1e-6), max=1.0))
             self.opt.step(scale)                                                         # :652
             self.opt.zero_grad()                                                         # :654
 
@@ -271,3 +283,11 @@ class PretrainStep:
         out = self._fwd_bwd(batch)
         self._apply_optimizer()
         return out
+
+
+def TuningStep(unet, e4t_encoder, text_encoder, placeholder_token_id, class_token_id, lr=1.6e-5, reg_lambda=1e-4,
+               max_grad_norm=1.0, **kw):
+    """One optimisation step of tuning_e4t.py:270-338 (BASELINE.json configs[3]): the pre-training step with every UNet
+    weight and the encoder trainable, reg_lambda 1e-4 (tuning_e4t.py:31) and gradient-norm clipping at 1.0 (:38)."""
+    return PretrainStep(unet, e4t_encoder, text_encoder, placeholder_token_id, class_token_id, lr=lr,
+                        reg_lambda=reg_lambda, tune_unet=True, max_grad_norm=max_grad_norm, **kw)

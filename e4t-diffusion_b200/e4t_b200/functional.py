@@ -62,26 +62,45 @@ def as_bf16(t):
 # ----------------------------------------------------------------------------------------------
 # dense layers
 # ----------------------------------------------------------------------------------------------
+def _wgrad_splits(m, C, R):
+    tiles = ((C + 127) // 128) * ((R + 127) // 128)
+    return max(1, min((m + 63) // 64, (2 * 148 + tiles - 1) // tiles))
+
+
 class LinearFn(torch.autograd.Function):
-    """y = x @ Wᵀ (+bias) (+residual).  W: bf16 (N,K) operand copy.  Backward: dX only (+ pass-through to residual)."""
+    """y = x @ Wᵀ (+bias) (+residual).  w: bf16 (N,K) operand copy of the fp32 master `wp` (an nn.Parameter of shape
+    (N,K) or (N,K,1,1), or None).  Backward: dX (+ pass-through to residual); and — only when the master weight / bias
+    require grad (tuning_e4t.py:139-146 trains every UNet weight, --unfreeze_clip_vision the ViT; pretrain_e4t.py leaves
+    them un-optimised, engine.PretrainStep freezes them) — dW = dYᵀ·X as a split-K tcgen05 GEMM (fp32) and
+    db = column sums of dY."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, residual):
+    def forward(ctx, x, w, bias, residual, wp=None):
         shp = x.shape
         x2 = _c(x).view(-1, shp[-1])
         res2 = None if residual is None else _c(residual).view(-1, w.shape[0])
         y = ops.gemm(x2, w, bias=bias, residual=res2)
-        ctx.save_for_backward(w)
+        need_dw = wp is not None and wp.requires_grad and torch.is_grad_enabled()
+        ctx.save_for_backward(w, x2 if need_dw else None)
         ctx.shp = shp
         ctx.has_res = residual is not None
+        ctx.wshape = None if wp is None else tuple(wp.shape)
         return y.view(*shp[:-1], w.shape[0])
 
     @staticmethod
     def backward(ctx, dy):
-        (w,) = ctx.saved_tensors
-        dy2 = _c(dy).view(-1, w.shape[0])
+        w, x2 = ctx.saved_tensors
+        N, K = w.shape
+        dy2 = _c(dy).view(-1, N)
         dx = ops.gemm(dy2, w, b_mn=True).view(ctx.shp) if ctx.needs_input_grad[0] else None
-        return dx, None, None, (dy if ctx.has_res else None)
+        db = dw = None
+        if ctx.needs_input_grad[2]:
+            db = ops.colsum_acc(dy2, torch.zeros(N, device=dy2.device, dtype=F32))
+        if len(ctx.needs_input_grad) > 4 and ctx.needs_input_grad[4] and x2 is not None:
+            dw = torch.zeros((N, K), device=dy2.device, dtype=F32)
+            ops.gemm(dy2, x2, a_mn=True, b_mn=True, out=dw, accumulate=True, splits=_wgrad_splits(x2.shape[0], N, K))
+            dw = dw.view(ctx.wshape)
+        return dx, None, db, (dy if ctx.has_res else None), dw
 
 
 class WOLinearFn(torch.autograd.Function):
@@ -144,21 +163,35 @@ class WOLinearBankFn(torch.autograd.Function):
 
 class Conv3x3Fn(torch.autograd.Function):
     """3x3/s1/p1 convolution on NHWC (+bias +per-image row add (time embedding) +residual).  Backward: dX via the same
-    implicit-GEMM kernel with the flipped/transposed taps; pass-through to residual."""
+    implicit-GEMM kernel with the flipped/transposed taps; pass-through to residual; and, when the fp32 master weight
+    `wp` (Cout,Cin,3,3) / bias / row add require grad (tuning), dW by the implicit-GEMM weight-gradient mode of the
+    engine (9 taps x split-K over the pixels), db = column sums of dY, d(row add) = per-image column sums of dY."""
 
     @staticmethod
-    def forward(ctx, x, w9, w9_dgrad, bias, rowgroup, residual):
-        y = ops.conv3x3(_c(x), w9, bias=bias, rowgroup=rowgroup, residual=None if residual is None else _c(residual))
-        ctx.save_for_backward(w9_dgrad)
+    def forward(ctx, x, w9, w9_dgrad, bias, rowgroup, residual, wp=None):
+        x = _c(x)
+        y = ops.conv3x3(x, w9, bias=bias, rowgroup=rowgroup, residual=None if residual is None else _c(residual))
+        need_dw = wp is not None and wp.requires_grad and torch.is_grad_enabled()
+        ctx.save_for_backward(w9_dgrad, x if need_dw else None)
         ctx.has_res = residual is not None
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        (w9_dgrad,) = ctx.saved_tensors
+        w9_dgrad, x = ctx.saved_tensors
         dy = _c(dy)
+        Bn, H, W, Cout = dy.shape
         dx = ops.conv3x3(dy, w9_dgrad) if ctx.needs_input_grad[0] else None
-        return dx, None, None, None, None, (dy if ctx.has_res else None)
+        db = drow = dw = None
+        dy2 = dy.view(-1, Cout)
+        if ctx.needs_input_grad[3]:
+            db = ops.colsum_acc(dy2, torch.zeros(Cout, device=dy.device, dtype=F32))
+        if ctx.needs_input_grad[4]:
+            drow = ops.colsum_acc(dy2, torch.zeros((Bn, Cout), device=dy.device, dtype=F32), rows_per_group=H * W)
+        if len(ctx.needs_input_grad) > 6 and ctx.needs_input_grad[6] and x is not None:
+            dw9 = ops.conv3x3_wgrad(x, dy)                                      # (9, Cout, Cin), tap = ky*3+kx
+            dw = dw9.view(3, 3, Cout, -1).permute(2, 3, 0, 1).contiguous()     # -> (Cout, Cin, 3, 3)
+        return dx, None, None, db, drow, (dy if ctx.has_res else None), dw
 
 
 class ResampleFn(torch.autograd.Function):
@@ -175,18 +208,53 @@ class ResampleFn(torch.autograd.Function):
 
 
 class ConvOutFn(torch.autograd.Function):
-    """UNet conv_out: NHWC bf16 -> NCHW fp32 (unet_2d_condition.py:557)."""
+    """UNet conv_out: NHWC bf16 -> NCHW fp32 (unet_2d_condition.py:557).  Weight/bias gradients only when trainable."""
 
     @staticmethod
     def forward(ctx, x, w, bias):
-        ctx.save_for_backward(w)
+        x = _c(x)
+        need_dw = w.requires_grad and torch.is_grad_enabled()
+        ctx.save_for_backward(w, x if need_dw else None)
         ctx.C = x.shape[-1]
-        return ops.conv_out_fwd(_c(x), w, bias)
+        return ops.conv_out_fwd(x, w.detach(), bias.detach())
 
     @staticmethod
     def backward(ctx, dy):
-        (w,) = ctx.saved_tensors
-        return ops.conv_out_bwd(_c(dy.float()), w, ctx.C), None, None
+        w, x = ctx.saved_tensors
+        dy = _c(dy.float())
+        dx = ops.conv_out_bwd(dy, w.detach(), ctx.C) if ctx.needs_input_grad[0] else None
+        dw = db = None
+        if ctx.needs_input_grad[1] and x is not None:
+            acc = ops.narrow_conv_wgrad(x, dy, -1)                              # [ci][co][tap]
+            dw = acc.permute(1, 0, 2).reshape(dy.shape[1], ctx.C, 3, 3).contiguous()
+        if ctx.needs_input_grad[2]:
+            db = dy.sum(dim=(0, 2, 3))
+        return dx, dw, db
+
+
+class ConvInFn(torch.autograd.Function):
+    """UNet conv_in: NCHW fp32 latents -> NHWC bf16 (unet_2d_condition.py:481).  The latent input never needs a gradient;
+    weight/bias gradients only when trainable."""
+
+    @staticmethod
+    def forward(ctx, sample, w, bias):
+        sample = _c(sample.detach().float())
+        need_dw = w.requires_grad and torch.is_grad_enabled()
+        ctx.save_for_backward(sample if need_dw else None)
+        ctx.wshape = tuple(w.shape)
+        return ops.conv_in_fwd(sample, w.detach(), bias.detach())
+
+    @staticmethod
+    def backward(ctx, dy):
+        (sample,) = ctx.saved_tensors
+        dy = _c(dy)
+        dw = db = None
+        if ctx.needs_input_grad[1] and sample is not None:
+            dw = ops.narrow_conv_wgrad(dy, sample, 1).view(ctx.wshape)          # [co][ci][tap]
+        if ctx.needs_input_grad[2]:
+            C = dy.shape[-1]
+            db = ops.colsum_acc(dy.view(-1, C), torch.zeros(C, device=dy.device, dtype=F32))
+        return None, dw, db
 
 
 # ----------------------------------------------------------------------------------------------
@@ -205,7 +273,12 @@ class GroupNormFn(torch.autograd.Function):
     def backward(ctx, dy):
         x, gamma, beta, stats = ctx.saved_tensors
         groups, eps, silu = ctx.cfg
-        return ops.groupnorm_bwd(x, _c(dy), gamma, beta, stats, groups, eps, silu), None, None, None, None, None
+        dy = _c(dy)
+        dx = ops.groupnorm_bwd(x, dy, gamma, beta, stats, groups, eps, silu) if ctx.needs_input_grad[0] else None
+        dg = db = None
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:      # affine parameters trainable (tuning)
+            dg, db = ops.groupnorm_param_grad(x, dy, stats, gamma.detach(), beta.detach(), groups, eps, silu)
+        return dx, dg, db, None, None, None
 
 
 class LayerNormFn(torch.autograd.Function):
@@ -220,7 +293,12 @@ class LayerNormFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         x, gamma, stats = ctx.saved_tensors
-        return ops.layernorm_bwd(x, _c(dy), gamma, stats, ctx.eps), None, None, None
+        dy = _c(dy)
+        dx = ops.layernorm_bwd(x, dy, gamma, stats, ctx.eps) if ctx.needs_input_grad[0] else None
+        dg = db = None
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:      # affine parameters trainable (tuning / unfrozen ViT)
+            dg, db = ops.layernorm_param_grad(x, dy, stats, gamma.detach())
+        return dx, dg, db, None
 
 
 class GEGLUFn(torch.autograd.Function):
@@ -234,6 +312,49 @@ class GEGLUFn(torch.autograd.Function):
     def backward(ctx, dout):
         (h,) = ctx.saved_tensors
         return ops.geglu_bwd(h, _c(dout))
+
+
+class ActFn(torch.autograd.Function):
+    """Elementwise activation on bf16: mode ops.ACT_GELU (open_clip ViT MLP), ops.ACT_QUICK_GELU (CLIP text MLP),
+    ops.ACT_LEAKY_RELU (E4TEncoder head)."""
+
+    @staticmethod
+    def forward(ctx, x, mode):
+        x = _c(x)
+        ctx.save_for_backward(x)
+        ctx.mode = mode
+        return ops.act_fwd(x, mode)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        return ops.act_bwd(x, _c(dy), ctx.mode), None
+
+
+class SmallAttentionFn(torch.autograd.Function):
+    """softmax(QKᵀ/sqrt(dh) [+ causal mask]) V for short sequences (N, M <= 128, dh <= 64) on the fused (B,N,3C)
+    projection output — the CLIP text tower's causal self-attention (modeling_clip.py:45-51)."""
+
+    @staticmethod
+    def forward(ctx, qkv, heads, scale, causal):
+        qkv = _c(qkv)
+        C = qkv.shape[-1] // 3
+        q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+        o, lse = ops.attn_small_fwd(q, k, v, heads, scale, causal)
+        ctx.save_for_backward(qkv, o, lse)
+        ctx.cfg = (heads, scale, causal)
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        qkv, o, lse = ctx.saved_tensors
+        heads, scale, causal = ctx.cfg
+        C = qkv.shape[-1] // 3
+        q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+        d = torch.empty_like(qkv)
+        ops.attn_small_bwd(q, k, v, o, _c(do), lse, heads, scale, causal, dq=d[..., :C], dk=d[..., C:2 * C],
+                           dv=d[..., 2 * C:])
+        return d, None, None, None
 
 
 # ----------------------------------------------------------------------------------------------
@@ -334,7 +455,7 @@ class WOEffectiveFn(torch.autograd.Function):
         wo = [t[n + 9 * i:n + 9 * (i + 1)] for i in range(n)]
         fac = t[n + 9 * n:]
         dW = _c(dW.float())
-        grads = []
+        grads, base_grads = [], []
         r0 = 0
         for i, (W, p) in enumerate(zip(Ws, wo)):
             v, w1, b1, w2, b2, Wc, bc, Wr, br = p
@@ -345,8 +466,13 @@ class WOEffectiveFn(torch.autograd.Function):
             dv, dw1, db1, dw2, db2, dWc, dbc, dWr, dbr = ops.wo_bwd(dW[r0:r0 + C], W, v, w1, w2, Wc, Wr, bc, vx,
                                                                   vy, a, b, s)
             grads += [dv, dw1.view_as(w1), db1, dw2.view_as(w2), db2, dWc, dbc, dWr, dbr]
+            if ctx.needs_input_grad[1 + i]:     # base projection weight trainable (tuning): dW = dW_eff ⊙ (1 + Δ)
+                delta = b[:, None] * a[None, :] + s[:, None] * bc[None, :] + br[:, None]
+                base_grads.append(dW[r0:r0 + C] * (1.0 + delta))
+            else:
+                base_grads.append(None)
             r0 += C
-        return (None,) + (None,) * n + tuple(grads)
+        return (None,) + tuple(base_grads) + tuple(grads)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -329,3 +329,115 @@ def attn_bwd(q, k, v, o, do, lse, heads, scale=None, dq=None, dk=None, dv=None, 
               c_ll(do.stride(1)), c_ll(_bs(do)), c_ll(dq.stride(1)), c_ll(_bs(dq)), c_ll(dk.stride(1)), c_ll(_bs(dk)),
               c_ll(dv.stride(1)), c_ll(_bs(dv)), c_float(scale), stream())
     return dq, dk, dv
+
+
+# ----------------------------------------------------------------------------------------------
+# small operators (csrc/small_ops.cu) and weight gradients
+# ----------------------------------------------------------------------------------------------
+ACT_GELU, ACT_QUICK_GELU, ACT_LEAKY_RELU = 0, 1, 2
+
+
+def act_fwd(x, mode):
+    assert x.dtype == BF16 and x.is_contiguous()
+    y = torch.empty_like(x)
+    _lib.call("e4t_act_fwd", ptr(x), ptr(y), c_ll(x.numel()), c_int(mode), stream())
+    return y
+
+
+def act_bwd(x, dy, mode):
+    assert x.dtype == BF16 and dy.dtype == BF16 and x.is_contiguous() and dy.is_contiguous()
+    dx = torch.empty_like(x)
+    _lib.call("e4t_act_bwd", ptr(x), ptr(dy), ptr(dx), c_ll(x.numel()), c_int(mode), stream())
+    return dx
+
+
+def colsum_acc(x2, out, rows_per_group=0):
+    """out[g][n] += sum of the rows of group g of x2 (bf16 (M,N), row stride = x2.stride(0)); out fp32, pre-initialised."""
+    assert x2.dtype == BF16 and x2.dim() == 2 and x2.stride(1) == 1 and out.dtype == F32 and out.is_contiguous()
+    _lib.call("e4t_colsum_acc", ptr(x2), ptr(out), c_ll(x2.shape[0]), c_int(x2.shape[1]), c_ll(x2.stride(0)),
+              c_ll(rows_per_group), stream())
+    return out
+
+
+def attn_small_fwd(q, k, v, heads, scale=None, causal=False):
+    """Short-sequence attention (N, M <= 128, dh <= 64) with optional causal mask; same layout as attn_fwd."""
+    assert q.dtype == BF16 and k.dtype == BF16 and v.dtype == BF16
+    assert q.stride(-1) == 1 and k.stride(-1) == 1 and v.stride(-1) == 1
+    Bn, N, C = q.shape
+    M = k.shape[1]
+    dh = C // heads
+    scale = dh ** -0.5 if scale is None else scale
+    o = torch.empty((Bn, N, C), device=q.device, dtype=BF16)
+    lse = torch.empty((Bn, heads, N), device=q.device, dtype=F32)
+    _lib.call("e4t_attn_small_fwd", ptr(q), ptr(k), ptr(v), ptr(o), ptr(lse), c_int(Bn), c_int(heads), c_int(N),
+              c_int(M), c_int(dh), c_ll(q.stride(1)), c_ll(_bs(q)), c_ll(k.stride(1)), c_ll(_bs(k)), c_ll(v.stride(1)),
+              c_ll(_bs(v)), c_ll(o.stride(1)), c_ll(_bs(o)), c_float(scale), c_int(int(causal)), stream())
+    return o, lse
+
+
+def attn_small_bwd(q, k, v, o, do, lse, heads, scale=None, causal=False, dq=None, dk=None, dv=None):
+    assert do.dtype == BF16 and do.stride(-1) == 1
+    Bn, N, C = q.shape
+    M = k.shape[1]
+    dh = C // heads
+    scale = dh ** -0.5 if scale is None else scale
+    dq = torch.empty((Bn, N, C), device=q.device, dtype=BF16) if dq is None else dq
+    dk = torch.empty((Bn, M, C), device=q.device, dtype=BF16) if dk is None else dk
+    dv = torch.empty((Bn, M, C), device=q.device, dtype=BF16) if dv is None else dv
+    _lib.call("e4t_attn_small_bwd", ptr(q), ptr(k), ptr(v), ptr(o), ptr(do), ptr(lse), ptr(dq), ptr(dk), ptr(dv),
+              c_int(Bn), c_int(heads), c_int(N), c_int(M), c_int(dh), c_ll(q.stride(1)), c_ll(_bs(q)),
+              c_ll(k.stride(1)), c_ll(_bs(k)), c_ll(v.stride(1)), c_ll(_bs(v)), c_ll(o.stride(1)), c_ll(_bs(o)),
+              c_ll(do.stride(1)), c_ll(_bs(do)), c_ll(dq.stride(1)), c_ll(_bs(dq)), c_ll(dk.stride(1)), c_ll(_bs(dk)),
+              c_ll(dv.stride(1)), c_ll(_bs(dv)), c_float(scale), c_int(int(causal)), stream())
+    return dq, dk, dv
+
+
+def layernorm_param_grad(x, dy, stats, gamma):
+    """(dgamma, dbeta) fp32 of LayerNorm given the forward's (mean, rstd) stats."""
+    C = x.shape[-1]
+    rows = x.numel() // C
+    dg = torch.zeros(C, device=x.device, dtype=F32)
+    db = torch.zeros(C, device=x.device, dtype=F32)
+    _lib.call("e4t_layernorm_param_grad", ptr(x), ptr(dy), ptr(stats), ptr(gamma), ptr(dg), ptr(db), c_ll(rows), c_int(C),
+              stream())
+    return dg, db
+
+
+def groupnorm_param_grad(x, dy, stats, gamma, beta, groups, eps, silu):
+    """(dgamma, dbeta) fp32 of GroupNorm(+SiLU); stats = the forward's (sum, sum of squares) per (image, group)."""
+    Bn, C = x.shape[0], x.shape[-1]
+    HW = x.numel() // (Bn * C)
+    n = float(HW * (C // groups))
+    mean = stats[..., 0] / n
+    var = (stats[..., 1] / n - mean * mean).clamp_min(0.0)
+    rstd = torch.rsqrt(var + eps)
+    mean_c = mean.repeat_interleave(C // groups, dim=1).contiguous()
+    rstd_c = rstd.repeat_interleave(C // groups, dim=1).contiguous()
+    dg = torch.zeros(C, device=x.device, dtype=F32)
+    db = torch.zeros(C, device=x.device, dtype=F32)
+    _lib.call("e4t_groupnorm_param_grad", ptr(x), ptr(dy), ptr(mean_c), ptr(rstd_c), ptr(gamma), ptr(beta), ptr(dg),
+              ptr(db), c_int(Bn), c_int(HW), c_int(C), c_int(int(silu)), stream())
+    return dg, db
+
+
+def narrow_conv_wgrad(wide, narrow, sgn):
+    """acc[w][n][tap] = sum wide[b,y,x,w] * narrow[b,n,y+sgn*(ky-1),x+sgn*(kx-1)] (weight gradients of conv_in / conv_out)."""
+    assert wide.dtype == BF16 and wide.is_contiguous() and narrow.dtype == F32 and narrow.is_contiguous()
+    Bn, H, W, Cw = wide.shape
+    Cn = narrow.shape[1]
+    assert narrow.shape == (Bn, Cn, H, W)
+    acc = torch.zeros((Cw, Cn, 9), device=wide.device, dtype=F32)
+    _lib.call("e4t_narrow_conv_wgrad", ptr(wide), ptr(narrow), ptr(acc), c_int(Bn), c_int(H), c_int(W), c_int(Cw),
+              c_int(Cn), c_int(sgn), stream())
+    return acc
+
+
+def conv3x3_wgrad(x, dy):
+    """dW9 fp32 (9, Cout, Cin) of a 3x3/s1/p1 convolution on NHWC bf16 (x: (B,H,W,Cin), dy: (B,H,W,Cout))."""
+    assert x.dtype == BF16 and dy.dtype == BF16 and x.is_contiguous() and dy.is_contiguous()
+    Bn, H, W, Cin = x.shape
+    Cout = dy.shape[-1]
+    dw9 = torch.zeros((9, Cout, Cin), device=x.device, dtype=F32)
+    _lib.call("e4t_conv3x3_wgrad", ptr(x), ptr(dy), ptr(dw9), c_int(Bn), c_int(H), c_int(W), c_int(Cin), c_int(Cout),
+              stream())
+    return dw9

@@ -24,10 +24,12 @@ class _WOProj(ctypes.Structure):
 
 class _BankFn(torch.autograd.Function):
     """forward: factors + W_eff for every projection; backward (runs after every projection's dX/dW GEMM, because they
-    all take `token` as an input): all WeightOffsets parameter gradients, written into the arena `.grad` views."""
+    all take `token` as an input): all WeightOffsets parameter gradients, accumulated into the arena `.grad` views.
+    Inputs: the 864 WeightOffsets parameters, then the 96 base projection weights — their gradient
+    dW = dW_eff ⊙ (1 + Δ) is returned only when they require grad (tuning_e4t.py trains them)."""
 
     @staticmethod
-    def forward(ctx, bank, *params):
+    def forward(ctx, bank, *tensors):
         ctx.bank = bank
         bank._launch_forward()
         return torch.zeros(1, device=bank.device, dtype=torch.float32)
@@ -35,8 +37,18 @@ class _BankFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, _dtoken):
         FN.WO_EPOCH += 1
-        ctx.bank._launch_backward()
-        return (None,) * (1 + len(ctx.bank.params))
+        bank = ctx.bank
+        bank._launch_backward()
+        n = len(bank.params)
+        base = []
+        for i, ((lin, wo), off) in enumerate(zip(bank.projs, bank._offsets)):
+            if ctx.needs_input_grad[1 + n + i]:
+                C, R = lin.out_features, lin.in_features
+                with torch.no_grad():
+                    base.append(bank.dweff[off:off + C * R].view(C, R) * (1.0 + wo()))
+            else:
+                base.append(None)
+        return (None,) * (1 + n) + tuple(base)
 
 
 class WOBank:
@@ -130,7 +142,7 @@ class WOBank:
                tuple(p._version for p in self.params[:9]))
         if self._key != key:
             if grad_on:
-                self._token = _BankFn.apply(self, *self.params)
+                self._token = _BankFn.apply(self, *self.params, *[l.weight for l, _ in self.projs])
             else:
                 self._launch_forward()
                 self._token = None

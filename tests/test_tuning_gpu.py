@@ -1,0 +1,212 @@
+"""Weight-gradient path (tuning_e4t.py trains EVERY UNet weight, --unfreeze_clip_vision the ViT; and
+accelerate's DDP wrapper in pretrain_e4t.py:410 expects a gradient for every requires_grad parameter).
+
+Kernel level: each parameter-gradient kernel against torch autograd of the same op in fp32 on bf16-representable inputs.
+Model level : every parameter gradient of the tiny UNet, and of one SD-v1.4-sized ResnetBlock2D + Transformer2DModel,
+against autograd of the CPU oracle (oracle/e4t_oracle.py, pinned to the reference's own modules); then the whole
+domain-tuning step (TuningStep == tuning_e4t.py:270-338) against an oracle run with torch AdamW + clip_grad_norm_."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import e4t_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(shape, g, s=0.5):
+    return (torch.randn(*shape, device="cuda", generator=g) * s).to(torch.bfloat16)
+
+
+def _rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+@pytest.mark.parametrize("M,N,K", [(4096, 320, 320), (1232, 768, 3072), (300, 64, 128)])
+def test_linear_weight_and_bias_grads(M, N, K):
+    from e4t_b200 import functional as FN
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    x = _mk((2, M // 2, K), g).requires_grad_(True)
+    wp = torch.nn.Parameter((torch.randn(N, K, device="cuda", generator=g) * 0.05).to(torch.bfloat16).float())
+    bp = torch.nn.Parameter(torch.randn(N, device="cuda", generator=g) * 0.1)
+    res = _mk((2, M // 2, N), g).requires_grad_(True)
+    dy = _mk((2, M // 2, N), g)
+    y = FN.LinearFn.apply(x, wp.detach().to(torch.bfloat16), bp, res, wp)
+    y.backward(dy)
+    xr = x.detach().float().requires_grad_(True)
+    wr, br = wp.detach().clone().requires_grad_(True), bp.detach().clone().requires_grad_(True)
+    (F.linear(xr, wr, br) + res.detach().float()).backward(dy.float())
+    assert _rel(wp.grad, wr.grad) < 2e-3 and _rel(bp.grad, br.grad) < 2e-3
+    assert _rel(x.grad, xr.grad) < 6e-3 and _rel(res.grad, dy) < 1e-6
+
+
+@pytest.mark.parametrize("B,H,Cin,Cout", [(2, 32, 64, 128), (2, 16, 320, 640), (4, 8, 128, 64), (1, 64, 64, 64)])
+def test_conv3x3_weight_bias_rowadd_grads(B, H, Cin, Cout):
+    from e4t_b200 import functional as FN
+    g = torch.Generator(device="cuda").manual_seed(H + Cin)
+    x = _mk((B, H, H, Cin), g).requires_grad_(True)
+    conv = torch.nn.Conv2d(Cin, Cout, 3, padding=1).cuda()
+    with torch.no_grad():
+        conv.weight.copy_(conv.weight.to(torch.bfloat16).float())
+    row = (torch.randn(B, Cout, device="cuda", generator=g) * 0.3).requires_grad_(True)
+    dy = _mk((B, H, H, Cout), g)
+    w9 = conv.weight.detach().permute(2, 3, 0, 1).reshape(9, Cout, Cin).to(torch.bfloat16).contiguous()
+    w9d = conv.weight.detach().flip(2, 3).permute(2, 3, 1, 0).reshape(9, Cin, Cout).to(torch.bfloat16).contiguous()
+    y = FN.Conv3x3Fn.apply(x, w9, w9d, conv.bias, row, None, conv.weight)
+    y.backward(dy)
+    xr = x.detach().float().permute(0, 3, 1, 2).requires_grad_(True)
+    wr, br = conv.weight.detach().clone().requires_grad_(True), conv.bias.detach().clone().requires_grad_(True)
+    rr = row.detach().clone().requires_grad_(True)
+    yr = F.conv2d(xr, wr, br, padding=1) + rr[:, :, None, None]
+    yr.backward(dy.float().permute(0, 3, 1, 2))
+    assert _rel(conv.weight.grad, wr.grad) < 3e-3, _rel(conv.weight.grad, wr.grad)
+    assert _rel(conv.bias.grad, br.grad) < 2e-3 and _rel(row.grad, rr.grad) < 2e-3
+    assert _rel(x.grad.permute(0, 3, 1, 2), xr.grad) < 6e-3
+
+
+@pytest.mark.parametrize("silu", [False, True])
+def test_groupnorm_layernorm_affine_grads(silu):
+    from e4t_b200 import functional as FN
+    g = torch.Generator(device="cuda").manual_seed(5)
+    B, HW, C, G = 3, 256, 320, 32
+    x = _mk((B, HW, C), g, 1.0).requires_grad_(True)
+    gam = torch.nn.Parameter(1 + 0.2 * torch.randn(C, device="cuda", generator=g))
+    bet = torch.nn.Parameter(0.2 * torch.randn(C, device="cuda", generator=g))
+    dy = _mk((B, HW, C), g)
+    FN.GroupNormFn.apply(x, gam, bet, G, 1e-5, silu).backward(dy)
+    xr = x.detach().float().requires_grad_(True)
+    gr, br = gam.detach().clone().requires_grad_(True), bet.detach().clone().requires_grad_(True)
+    yr = F.group_norm(xr.permute(0, 2, 1), G, gr, br, 1e-5).permute(0, 2, 1)
+    (F.silu(yr) if silu else yr).backward(dy.float())
+    assert _rel(gam.grad, gr.grad) < 4e-3 and _rel(bet.grad, br.grad) < 4e-3
+    if not silu:
+        x2 = _mk((500, 768), g, 1.0).requires_grad_(True)
+        g2 = torch.nn.Parameter(1 + 0.2 * torch.randn(768, device="cuda", generator=g))
+        b2 = torch.nn.Parameter(0.2 * torch.randn(768, device="cuda", generator=g))
+        dy2 = _mk((500, 768), g)
+        FN.LayerNormFn.apply(x2, g2, b2, 1e-5).backward(dy2)
+        xr2 = x2.detach().float().requires_grad_(True)
+        gr2, br2 = g2.detach().clone().requires_grad_(True), b2.detach().clone().requires_grad_(True)
+        F.layer_norm(xr2, (768,), gr2, br2, 1e-5).backward(dy2.float())
+        assert _rel(g2.grad, gr2.grad) < 4e-3 and _rel(b2.grad, br2.grad) < 4e-3
+
+
+def test_conv_in_out_weight_grads():
+    from e4t_b200 import functional as FN
+    g = torch.Generator(device="cuda").manual_seed(6)
+    lat = torch.randn(2, 4, 16, 16, device="cuda", generator=g)
+    ci = torch.nn.Conv2d(4, 64, 3, padding=1).cuda()
+    dy = _mk((2, 16, 16, 64), g)
+    FN.ConvInFn.apply(lat, ci.weight, ci.bias).backward(dy)
+    wr, br = ci.weight.detach().clone().requires_grad_(True), ci.bias.detach().clone().requires_grad_(True)
+    F.conv2d(lat, wr, br, padding=1).backward(dy.float().permute(0, 3, 1, 2))
+    assert _rel(ci.weight.grad, wr.grad) < 2e-3 and _rel(ci.bias.grad, br.grad) < 2e-3
+    co = torch.nn.Conv2d(64, 4, 3, padding=1).cuda()
+    x = _mk((2, 16, 16, 64), g).requires_grad_(True)
+    dyo = torch.randn(2, 4, 16, 16, device="cuda", generator=g)
+    FN.ConvOutFn.apply(x, co.weight, co.bias).backward(dyo)
+    xr = x.detach().float().permute(0, 3, 1, 2).requires_grad_(True)
+    wr, br = co.weight.detach().clone().requires_grad_(True), co.bias.detach().clone().requires_grad_(True)
+    F.conv2d(xr, wr, br, padding=1).backward(dyo)
+    assert _rel(co.weight.grad, wr.grad) < 2e-3 and _rel(co.bias.grad, br.grad) < 1e-4
+    assert _rel(x.grad.permute(0, 3, 1, 2), xr.grad) < 6e-3
+
+
+@pytest.mark.parametrize("B,H,N,dh,causal", [(2, 12, 77, 64, True), (2, 4, 77, 32, False), (1, 8, 128, 64, True),
+                                             (3, 2, 5, 16, True)])
+def test_small_attention_fwd_bwd(B, H, N, dh, causal):
+    from e4t_b200 import functional as FN
+    g = torch.Generator(device="cuda").manual_seed(N + dh)
+    C = H * dh
+    qkv = _mk((B, N, 3 * C), g).requires_grad_(True)
+    do = _mk((B, N, C), g)
+    FN.SmallAttentionFn.apply(qkv, H, dh ** -0.5, causal).backward(do)
+    r = qkv.detach().float().requires_grad_(True)
+    q, k, v = (t.view(B, N, H, dh).transpose(1, 2) for t in r.chunk(3, dim=-1))
+    o = F.scaled_dot_product_attention(q, k, v, is_causal=causal).transpose(1, 2).reshape(B, N, C)
+    o.backward(do.float())
+    got = FN.SmallAttentionFn.apply(qkv.detach(), H, dh ** -0.5, causal)
+    assert _rel(got, o) < 6e-3 and _rel(qkv.grad, r.grad) < 1e-2
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_activations(mode):
+    from e4t_b200 import functional as FN
+    g = torch.Generator(device="cuda").manual_seed(mode)
+    x = _mk((64, 1024), g, 2.0).requires_grad_(True)
+    dy = _mk((64, 1024), g)
+    FN.ActFn.apply(x, mode).backward(dy)
+    xr = x.detach().float().requires_grad_(True)
+    yr = (F.gelu(xr), xr * torch.sigmoid(1.702 * xr), F.leaky_relu(xr, 0.01))[mode]
+    yr.backward(dy.float())
+    assert _rel(FN.ActFn.apply(x.detach(), mode), yr) < 4e-3 and _rel(x.grad, xr.grad) < 5e-3
+
+
+def _unet_all_param_grads(cfg, seed, hw, B):
+    from e4t.models.unet_2d_condition import UNet2DConditionModel
+    m = UNet2DConditionModel(**O.ref_unet_kwargs(cfg))
+    sd = O.synth_state_dict(O.unet_param_shapes(cfg), seed)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda()
+    x, t, ehs, w, _ = O.golden_unet_inputs(cfg, B, seed, hw)
+    (m(x.cuda(), t.cuda(), ehs.cuda()).sample * w.cuda()).sum().backward()
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    (O.unet_forward(sdg, cfg, x, t, ehs) * w).sum().backward()
+    named = dict(m.named_parameters())
+    return {k: _rel(named[k].grad, sdg[k].grad) for k in sd if sdg[k].grad is not None}, named
+
+
+def test_tiny_unet_every_parameter_gradient_vs_oracle_autograd():
+    errs, named = _unet_all_param_grads(O.TINY_UNET, 7, 16, 2)
+    assert all(p.grad is not None for p in named.values()), [k for k, p in named.items() if p.grad is None][:5]
+    base = {k: v for k, v in errs.items() if "wo" not in k}
+    srt = sorted(base.values())
+    worst = max(base, key=base.get)
+    print(f"[tuning grads tiny] {len(base)} base params: median {srt[len(srt)//2]:.3e} p90 {srt[int(.9*len(srt))]:.3e} "
+          f"max {srt[-1]:.3e} ({worst})")
+    assert srt[len(srt) // 2] < 3e-2 and srt[-1] < 0.15
+
+
+def test_tuning_step_tiny_vs_oracle_adamw_with_clipping():
+    from e4t.encoder import E4TEncoder
+    from e4t.models.modeling_clip import CLIPTextConfig, CLIPTextModel
+    from e4t.models.unet_2d_condition import UNet2DConditionModel
+    from e4t_b200.engine import TuningStep
+    ucfg, vcfg, tcfg = O.TINY_UNET, O.VIT_TINY, O.CLIP_TEXT_TINY
+    fd = O.pooled_feature_dim(ucfg)
+    sd_u = O.synth_state_dict(O.unet_param_shapes(ucfg), 21)
+    sd_e = O.synth_state_dict(O.encoder_param_shapes(vcfg, fd, tcfg["width"], 129), 22)
+    sd_t = O.synth_state_dict(O.text_param_shapes(tcfg), 23)
+    unet = UNet2DConditionModel(**O.ref_unet_kwargs(ucfg)); unet.load_state_dict(sd_u)
+    enc = E4TEncoder(arch="ViT-tiny-test", word_embedding_dim=tcfg["width"], n_odd_layers=129, unet_feature_dim=fd)
+    enc.load_state_dict(sd_e)
+    text = CLIPTextModel(CLIPTextConfig(vocab_size=tcfg["vocab"], hidden_size=tcfg["width"],
+                                        intermediate_size=tcfg["mlp"], num_hidden_layers=tcfg["layers"],
+                                        num_attention_heads=tcfg["heads"]))
+    text.load_state_dict(sd_t)
+    step = TuningStep(unet.cuda(), enc.cuda(), text.cuda(), O.PLACEHOLDER_ID, class_token_id=320, lr=2e-4,
+                      weight_dtype=torch.float32)
+    assert all(p.requires_grad for p in unet.parameters())                     # tuning_e4t.py:139-146
+    train = [k for k in sd_u] + [k for k in sd_e if not k.startswith("clip_vision.")]
+    plist = [sd_u[k].requires_grad_(True) for k in sd_u] + [sd_e[k].requires_grad_(True) for k in sd_e
+                                                            if not k.startswith("clip_vision.")]
+    opt = torch.optim.AdamW(plist, lr=2e-4, betas=(0.9, 0.999), weight_decay=1e-2, eps=1e-8)
+    base = O.synth_batch(2, seed=77, latent_hw=16, image_hw=64)                # ONE image batch, re-noised every step
+    lo, lg = [], []
+    for it in range(5):
+        gen = torch.Generator().manual_seed(900 + it)
+        batch = dict(base, noise=torch.randn(base["latents"].shape, generator=gen),
+                     timesteps=torch.randint(0, 1000, (2,), generator=gen))
+        ref = O.pretrain_step(sd_u, ucfg, sd_e, vcfg, sd_t, tcfg, batch, class_token_id=320, reg_lambda=1e-4)
+        opt.zero_grad()
+        ref["loss"].backward()
+        torch.nn.utils.clip_grad_norm_(plist, 1.0)
+        opt.step()
+        out = step({k: v.cuda() for k, v in batch.items()})
+        lo.append(ref["loss"].item()); lg.append(out["loss"].item())
+    print("[tuning step] oracle", [round(v, 5) for v in lo], "cuda", [round(v, 5) for v in lg])
+    for a, b in zip(lo, lg):
+        assert abs(a - b) <= 3e-2 * abs(a) + 1e-4, (lo, lg)

@@ -8,9 +8,8 @@ import json
 for r in json.load(open("gpurun_out/attn_bench.json")):
     print(r["shape"], {k: (v["ms"], v["frac"], round(v["err_vs_legacy"], 5)) for k, v in r.items() if k.startswith("fwd")})
 PY
-for v in "p0" "h"; do
+for v in "p0" "b"; do
   E4T_ATTN_FWD2=$v timeout 120 ncu --set full --import-source on --clock-control none -k regex:attn_fwd2 -c 1 \
       -o gpurun_out/r2c3_fwd2_$v -f python tools/prof_attn.py > gpurun_out/r2c3_ncu_$v.log 2>&1
   echo "ncu $v rc=$?"
 done
-timeout 500 python -m pytest tests/test_e2e_gpu.py -m gpu -x -q -s --timeout 400 -p no:cacheprovider > gpurun_out/r2c3_e2e.log 2>&1; echo "e2e rc=$?"; grep -E "^\[|passed|failed" gpurun_out/r2c3_e2e.log | cut -c1-400

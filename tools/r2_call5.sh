@@ -1,0 +1,11 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 200 python -m pytest tests/test_variants_gpu.py -m gpu -x -q --timeout 120 -p no:cacheprovider -k "forward_variants" > gpurun_out/r2c5_variants.log 2>&1; echo "variants rc=$?"; tail -3 gpurun_out/r2c5_variants.log
+timeout 240 python tools/attn_bench.py fwd > gpurun_out/r2c5_attn_bench.log 2>&1; echo "attn_bench rc=$?"
+python - <<'PY'
+import json
+for r in json.load(open("gpurun_out/attn_bench.json"))[:2]:
+    print(r["shape"], {k: (v["ms"], v["frac"], round(v["err_vs_legacy"], 5)) for k, v in r.items() if k.startswith("fwd")})
+PY
+E4T_ATTN_FWD2=p0 timeout 120 ncu --set full --import-source on --clock-control none -k regex:attn_fwd2 -c 1 -o gpurun_out/r2c5_fwd2_p0 -f python tools/prof_attn.py > gpurun_out/r2c5_ncu_p0.log 2>&1; echo "ncu rc=$?"
+timeout 600 python -m pytest tests/test_tuning_gpu.py tests/test_dropin_gpu.py -m gpu -q -s --timeout 300 -p no:cacheprovider > gpurun_out/r2c5_tuning.log 2>&1; echo "tuning tests rc=$?"; grep -E "^\[|passed|failed|Error|FAILED|assert" gpurun_out/r2c5_tuning.log | cut -c1-300 | head -40
