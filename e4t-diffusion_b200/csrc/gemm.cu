@@ -32,7 +32,7 @@ struct GemmArgs {
   const bf16* residual;  // [M][ldr] bf16 or null
   long long ldr, res_bstride;
   float alpha;
-  int debug;      // E4T_GEMM_DEBUG bit0: skip epilogue body; bit1: skip tmem loads only
+  int debug;      // E4T_GEMM_DEBUG probes: 1 skip epilogue body, 4 skip output staging, 8 no TMA loads, 16 no MMAs
   int tma_store;  // bf16 output through smem staging + TMA store (coalesced, asynchronous)
   int epi_plain;  // default on (E4T_GEMM_EPI_PLAIN=0 disables): separate slab loop for outputs without alpha/bias/rowgroup/residual
 };
@@ -110,6 +110,9 @@ e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
           mbar_wait(&empty_bar[s], ph ^ 1u);
           uint8_t* sA = smem + (size_t)s * stage_bytes;
           uint8_t* sB = sA + kATileBytes;
+          if (g.debug & 8) {          // probe: no operand traffic at all (MMA + barrier rate on stale smem)
+            if (elect_one()) mbar_arrive(&full_bar[s]);
+          } else
           if (elect_one()) {
           mbar_expect_tx(&full_bar[s], (uint32_t)stage_bytes);
           if (g.conv == 2) {
@@ -180,10 +183,12 @@ e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
           if (elect_one()) {
             const uint64_t da = dA0 + (uint64_t)((uint32_t)s * stage_units);
             const uint64_t db = dB0 + (uint64_t)((uint32_t)s * stage_units);
+            if (!(g.debug & 16)) {      // probe bit 16: no MMAs (TMA delivery rate alone)
 #pragma unroll
             for (int k = 0; k < kBK / 16; ++k)
               umma_bf16(d_tmem, da + (uint64_t)(k * a_step), db + (uint64_t)(k * b_step), idesc,
                         (kc > kc0 || k > 0) ? 1u : 0u);
+            }
             umma_commit(&empty_bar[s]);  // frees the smem stage when these MMAs retire
           }
           __syncwarp();

@@ -11,14 +11,16 @@ feature_linear([hs_i,u]) = hs_i·Wf[:, :W]ᵀ + u·Wf[:, W:]ᵀ + bf, so the hea
 broadcast add and ONE batched GEMM over the stacked first_linears.  The 129 first_linears parameters are views of
 one stacked (129,W,W) storage (state-dict keys unchanged) so no per-step stacking copy is needed.
 
-The ViT tower is frozen by default (freeze_clip_vision=True) and, being ranked below the UNet kernels in SURVEY.md
-§8, runs on stock torch ops (cuBLAS + SDPA) in bf16; random-init construction never touches the network."""
+Everything runs on the sm_100a kernels (round 2): the ViT tower (frozen by default; with freeze_clip_vision=False —
+`--unfreeze_clip_vision` — every tower weight receives its gradient from the same kernels), and the head.  Random-init
+construction never touches the network."""
 import torch
 import torch.nn.functional as F
 from torch import nn
 
 from e4t._mixins import ConfigMixin, ModelMixin, register_to_config
 from e4t_b200 import functional as FN
+from e4t_b200 import ops
 
 _VIT_ARCHS = {
     # arch: (width, layers, heads, mlp, patch, image)
@@ -27,6 +29,15 @@ _VIT_ARCHS = {
     "ViT-B-32": (768, 12, 12, 3072, 32, 224),
     "ViT-tiny-test": (64, 2, 4, 128, 14, 224),
 }
+
+
+def _bf16(p):
+    """bf16 operand copy of a (possibly trainable) fp32 master, cached until the master changes."""
+    return FN.prepared(p, "bf16", lambda t: t.to(torch.bfloat16).contiguous())
+
+
+def _f32(p):
+    return p if p.dtype == torch.float32 else FN.prepared(p, "f32", lambda t: t.float().contiguous())
 
 
 class _MHA(nn.Module):
@@ -40,13 +51,12 @@ class _MHA(nn.Module):
         self.out_proj = nn.Linear(width, width)
         nn.init.xavier_uniform_(self.in_proj_weight)
 
-    def forward(self, x, cast):
-        B, N, W = x.shape
-        q, k, v = F.linear(x, cast(self.in_proj_weight), cast(self.in_proj_bias)).chunk(3, dim=-1)
-        h = self.heads
-        q, k, v = (t.view(B, N, h, W // h).transpose(1, 2) for t in (q, k, v))
-        o = F.scaled_dot_product_attention(q, k, v)
-        return F.linear(o.transpose(1, 2).reshape(B, N, W), cast(self.out_proj.weight), cast(self.out_proj.bias))
+    def forward(self, h, residual):
+        """in_proj (one fused QKV GEMM, bias in the epilogue) -> fused attention core -> out_proj (+bias +residual)."""
+        W = h.shape[-1]
+        qkv = FN.LinearFn.apply(h, _bf16(self.in_proj_weight), _f32(self.in_proj_bias), None, self.in_proj_weight)
+        o = FN.AttentionFn.apply(qkv, None, self.heads, (W // self.heads) ** -0.5)
+        return FN.LinearFn.apply(o, _bf16(self.out_proj.weight), _f32(self.out_proj.bias), residual, self.out_proj.weight)
 
 
 class _MLP(nn.Module):
@@ -55,6 +65,15 @@ class _MLP(nn.Module):
         self.c_fc = nn.Linear(width, mlp)
         self.gelu = nn.GELU()
         self.c_proj = nn.Linear(mlp, width)
+
+    def forward(self, h, residual):
+        h = FN.LinearFn.apply(h, _bf16(self.c_fc.weight), _f32(self.c_fc.bias), None, self.c_fc.weight)
+        h = FN.ActFn.apply(h, ops.ACT_GELU)
+        return FN.LinearFn.apply(h, _bf16(self.c_proj.weight), _f32(self.c_proj.bias), residual, self.c_proj.weight)
+
+
+def _ln(norm, x):
+    return FN.LayerNormFn.apply(x, _f32(norm.weight), _f32(norm.bias), norm.eps)
 
 
 class _ResBlock(nn.Module):
@@ -65,12 +84,9 @@ class _ResBlock(nn.Module):
         self.ln_2 = nn.LayerNorm(width)
         self.mlp = _MLP(width, mlp)
 
-    def forward(self, x, cast):
-        h = F.layer_norm(x, (x.shape[-1],), cast(self.ln_1.weight), cast(self.ln_1.bias), 1e-5)
-        x = x + self.attn(h, cast)
-        h = F.layer_norm(x, (x.shape[-1],), cast(self.ln_2.weight), cast(self.ln_2.bias), 1e-5)
-        h = F.gelu(F.linear(h, cast(self.mlp.c_fc.weight), cast(self.mlp.c_fc.bias)))
-        return x + F.linear(h, cast(self.mlp.c_proj.weight), cast(self.mlp.c_proj.bias))
+    def forward(self, x):
+        x = self.attn(_ln(self.ln_1, x), x)            # x + attn(ln_1(x)): the residual add rides in out_proj's epilogue
+        return self.mlp(_ln(self.ln_2, x), x)          # x + mlp(ln_2(x))
 
 
 class _Transformer(nn.Module):
@@ -80,14 +96,22 @@ class _Transformer(nn.Module):
 
 
 class VisionTransformer(nn.Module):
-    """open_clip VisionTransformer with proj=None, output_tokens=True: returns (ln_post(cls), patch tokens)."""
+    """open_clip VisionTransformer with proj=None, output_tokens=True: returns (ln_post(cls), patch tokens), on the
+    sm_100a kernels: patch embedding as one GEMM over unfolded 14x14 patches, LayerNorm kernel, fused-QKV tcgen05 GEMMs
+    with bias/residual epilogues, the two-tile attention forward (N = 257, 16 heads x 80), GELU kernel.
 
-    def __init__(self, width, layers, heads, mlp, patch, image):
+    `ln_post_on_tokens`: open_clip changed what `output_tokens=True` returns — up to 2.2x the patch tokens come back
+    WITHOUT ln_post, later releases apply ln_post to them first (SURVEY.md §8 a-12).  The reference pins no version;
+    the default is the contemporaneous behaviour (no ln_post on the tokens)."""
+
+    def __init__(self, width, layers, heads, mlp, patch, image, ln_post_on_tokens=False):
         super().__init__()
         self.output_tokens = True
         self.proj = None
         self.patch = patch
+        self.ln_post_on_tokens = ln_post_on_tokens
         grid = image // patch
+        self.grid = grid
         self.conv1 = nn.Conv2d(3, width, kernel_size=patch, stride=patch, bias=False)
         scale = width ** -0.5
         self.class_embedding = nn.Parameter(scale * torch.randn(width))
@@ -96,23 +120,39 @@ class VisionTransformer(nn.Module):
         self.transformer = _Transformer(width, layers, heads, mlp)
         self.ln_post = nn.LayerNorm(width)
 
+    def _patch_weight(self):
+        """conv1 weight as a (W, 3*p*p padded to a multiple of 8) bf16 GEMM operand (TMA row strides are 16-byte units)."""
+        def prep(w):
+            w2 = w.reshape(w.shape[0], -1)
+            kp = (w2.shape[1] + 7) // 8 * 8
+            out = torch.zeros((w2.shape[0], kp), device=w.device, dtype=torch.bfloat16)
+            out[:, :w2.shape[1]] = w2.to(torch.bfloat16)
+            return out
+        return FN.prepared(self.conv1.weight, "patch_bf16", prep)
+
     def forward(self, x, compute_dtype=torch.bfloat16):
+        if not x.is_cuda:
+            from e4t_b200._lib import E4TError
+            raise E4TError("e4t VisionTransformer runs on the sm_100a kernels only (no CPU fallback)")
         trainable = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
-        if trainable:   # --unfreeze_clip_vision: differentiable casts of the fp32 masters
-            cast = lambda p: p.to(compute_dtype)
-        else:           # frozen: cached bf16 operand copies
-            cast = lambda p: FN.prepared(p, ("cast", compute_dtype), lambda t: t.to(compute_dtype).contiguous())
-        W = self.conv1.out_channels
+        W, p, g = self.conv1.out_channels, self.patch, self.grid
+        B = x.shape[0]
         with torch.set_grad_enabled(trainable):
-            x = F.conv2d(x.to(compute_dtype), cast(self.conv1.weight), stride=self.patch)
-            x = x.reshape(x.shape[0], W, -1).permute(0, 2, 1)
-            cls = cast(self.class_embedding).expand(x.shape[0], 1, W)
-            x = torch.cat([cls, x], dim=1) + cast(self.positional_embedding)
-            x = F.layer_norm(x, (W,), cast(self.ln_pre.weight), cast(self.ln_pre.bias), 1e-5)
+            wp = self._patch_weight()
+            # conv 14x14 / stride 14 == GEMM over unfolded patches (pixels have no gradient)
+            cols = x.detach().reshape(B, 3, g, p, g, p).permute(0, 2, 4, 1, 3, 5).reshape(B, g * g, 3 * p * p)
+            a = torch.zeros((B, g * g, wp.shape[1]), device=x.device, dtype=torch.bfloat16)
+            a[..., :3 * p * p] = cols
+            tok = FN.LinearFn.apply(a, wp, None, None, self.conv1.weight)                       # (B, g*g, W)
+            cls = self.class_embedding.to(torch.bfloat16).expand(B, 1, W)
+            h = torch.cat([cls, tok], dim=1) + self.positional_embedding.to(torch.bfloat16)
+            h = _ln(self.ln_pre, h)
             for blk in self.transformer.resblocks:
-                x = blk(x, cast)
-            pooled = F.layer_norm(x[:, 0], (W,), cast(self.ln_post.weight), cast(self.ln_post.bias), 1e-5)
-            tokens = x[:, 1:]
+                h = blk(h)
+            pooled = _ln(self.ln_post, h[:, 0])
+            tokens = h[:, 1:]
+            if self.ln_post_on_tokens:
+                tokens = _ln(self.ln_post, tokens)
         return pooled, tokens
 
 
@@ -125,7 +165,8 @@ class E4TEncoder(ModelMixin, ConfigMixin):
             raise ValueError(f"unknown CLIP vision arch {arch}; known: {sorted(_VIT_ARCHS)}")
         width, layers, heads, mlp, patch, image = _VIT_ARCHS[arch]
         # random-init tower; pretrained weights arrive through load_state_dict / e4t.utils.load_e4t_encoder
-        self.clip_vision = VisionTransformer(width, layers, heads, mlp, patch, image)
+        self.clip_vision = VisionTransformer(width, layers, heads, mlp, patch, image,
+                                             ln_post_on_tokens=bool(kwargs.get("ln_post_on_tokens", False)))
         if freeze_clip_vision:
             self.clip_vision.requires_grad_(False)
         unet_feature_dim = int(kwargs.get("unet_feature_dim", 10880))       # hard-coded 10880 at encoder.py:102
@@ -210,20 +251,30 @@ class E4TEncoder(ModelMixin, ConfigMixin):
             u = FN.MeanPoolCatFn.apply(*maps)                                                    # encoder.py:147-148
         else:   # foreign tensors (e.g. NCHW fp32 from another UNet implementation)
             u = torch.cat([m.float().mean(dim=(2, 3)) for m in unet_down_block_samples], dim=-1)
-        u = self.unet_feature_embedder(u)                                                        # :149
+        bf = torch.bfloat16
+        fe0, fe2 = self.unet_feature_embedder[0], self.unet_feature_embedder[2]
+        u = FN.LinearFn.apply(u.to(bf), _bf16(fe0.weight), fe0.bias, None, fe0.weight)               # :149  (B,W)
+        u = FN.LinearFn.apply(FN.ActFn.apply(u, ops.ACT_LEAKY_RELU), _bf16(fe2.weight), fe2.bias, None, fe2.weight)
         pooled, tokens = self.clip_vision(self.preprocess(x))                                    # :153-154
-        hs = torch.cat([pooled.unsqueeze(1), tokens[:, 1::2, :]], dim=1).float()                 # :155-156  (B,n,W)
-        n, W = hs.shape[1], hs.shape[2]
+        hs = torch.cat([pooled.unsqueeze(1), tokens[:, 1::2, :]], dim=1)                         # :155-156  (B,n,W)
+        B, n, W = hs.shape
         if n != len(self.first_linears):
             raise ValueError(f"{n} CLIP states but {len(self.first_linears)} first_linears")
-        wf, bf = self.feature_linear.weight, self.feature_linear.bias
-        h = F.linear(hs, wf[:, :W]) + (F.linear(u, wf[:, W:]) + bf).unsqueeze(1)                 # :160 for all i
+        fl = self.feature_linear
+        # feature_linear(cat[hs_i, u]) for all i at once: one (B*n, 2W) x (2W, W) GEMM                       :160
+        h = FN.LinearFn.apply(torch.cat([hs, u.unsqueeze(1).expand(B, n, W)], dim=-1), _bf16(fl.weight), fl.bias, None,
+                              fl.weight)
         wst, bst = self._stacked()
         if torch.is_grad_enabled() and self.first_linears[0].weight.requires_grad:
             wst, bst = _StackedParams.apply(self, wst, bst, *[p for l in self.first_linears for p in (l.weight, l.bias)])
-        out = torch.baddbmm(bst.unsqueeze(1), h.transpose(0, 1), wst.transpose(1, 2))            # :161 (n,B,W)
-        out = self.act(out.mean(dim=0))                                                          # :163-166
-        return self.final_linear(out)                                                            # :168
+        # the 129 first_linears as ONE batched GEMM; their biases enter through the mean (mean_i(b_i) is exact)  :161-166
+        w16 = FN.prepared(self.first_linears[0].weight, ("stack_bf16", n),
+                          lambda t: self._stacked()[0].detach().to(bf).contiguous())
+        out = FN.BatchedLinearFn.apply(h.transpose(0, 1), w16, wst)                               # (n,B,W)
+        out = out.float().mean(dim=0) + bst.float().mean(dim=0)
+        out = FN.ActFn.apply(out.to(bf), ops.ACT_LEAKY_RELU)                                      # :167
+        fin = self.final_linear
+        return FN.LinearFn.apply(out, _bf16(fin.weight), fin.bias, None, fin.weight).float()      # :168
 
 
 class _StackedParams(torch.autograd.Function):

@@ -2,8 +2,11 @@
 text_model.embeddings.{token,position}_embedding, encoder.layers.{i}.{layer_norm1,self_attn.{q,k,v,out}_proj,
 layer_norm2,mlp.fc1,mlp.fc2}, final_layer_norm; causal mask; quick_gelu).
 
-Frozen weights, but dX must flow to the injected placeholder row (pretrain_e4t.py:630-634).  SURVEY.md §8 a-14 ranks
-this tower "next": it runs on stock torch ops (cuBLAS + SDPA) in the module's dtype, not on the e4t_b200 kernels."""
+Frozen weights, but dX must flow to the injected placeholder row (pretrain_e4t.py:630-634).  On CUDA the tower runs on
+the e4t_b200 kernels (round 2): LayerNorm kernel, one fused q|k|v tcgen05 GEMM with bias, the
+short-sequence causal attention kernel (77 tokens), out_proj / fc2 GEMMs with bias + residual epilogues, quick-GELU
+kernel; every Function returns dX.  CPU tensors (tokenizer-side utilities, tests of the module surface) take the plain
+torch path below — it is not used by any GPU step."""
 import json
 import os
 from dataclasses import dataclass
@@ -14,6 +17,20 @@ import torch.nn.functional as F
 from torch import nn
 
 from e4t._mixins import BaseOutput
+from e4t_b200 import functional as FN
+from e4t_b200 import ops
+
+
+def _bf16(p):
+    return FN.prepared(p, "bf16", lambda t: t.to(torch.bfloat16).contiguous())
+
+
+def _f32(p):
+    return p if p.dtype == torch.float32 else FN.prepared(p, "f32", lambda t: t.float().contiguous())
+
+
+def _ln_k(norm, x):
+    return FN.LayerNormFn.apply(x, _f32(norm.weight), _f32(norm.bias), norm.eps)
 
 
 @dataclass
@@ -58,6 +75,24 @@ class _Attention(nn.Module):
         self.heads = cfg.num_attention_heads
         self.q_proj, self.k_proj, self.v_proj, self.out_proj = (nn.Linear(d, d) for _ in range(4))
 
+    def _qkv(self):
+        """q|k|v projection weights row-concatenated into one GEMM operand (cached bf16 copy) + fp32 bias."""
+        ps = (self.q_proj, self.k_proj, self.v_proj)
+        w = FN.prepared(self.q_proj.weight, ("qkv_bf16", self.k_proj.weight._version, self.v_proj.weight._version),
+                        lambda t: torch.cat([p.weight.detach() for p in ps], dim=0).to(torch.bfloat16).contiguous())
+        b = FN.prepared(self.q_proj.bias, ("qkv_bias", self.k_proj.bias._version, self.v_proj.bias._version),
+                        lambda t: torch.cat([p.bias.detach() for p in ps], dim=0).float().contiguous())
+        return w, b
+
+    def forward_kernels(self, h, residual):
+        D = h.shape[-1]
+        if any(p.weight.requires_grad for p in (self.q_proj, self.k_proj, self.v_proj, self.out_proj)):
+            raise NotImplementedError("--train_text_encoder is not supported: the CLIP text tower is frozen on the E4T path")
+        w, b = self._qkv()
+        qkv = FN.LinearFn.apply(h, w, b, None, None)
+        o = FN.SmallAttentionFn.apply(qkv, self.heads, (D // self.heads) ** -0.5, True)   # causal (modeling_clip.py:45-47)
+        return FN.LinearFn.apply(o, _bf16(self.out_proj.weight), _f32(self.out_proj.bias), residual, None)
+
     def forward(self, x):
         B, N, D = x.shape
         h = self.heads
@@ -72,6 +107,11 @@ class _MLP(nn.Module):
         self.fc1 = nn.Linear(cfg.hidden_size, cfg.intermediate_size)
         self.fc2 = nn.Linear(cfg.intermediate_size, cfg.hidden_size)
         self.act = cfg.hidden_act
+
+    def forward_kernels(self, h, residual):
+        h = FN.LinearFn.apply(h, _bf16(self.fc1.weight), _f32(self.fc1.bias), None, None)
+        h = FN.ActFn.apply(h, ops.ACT_QUICK_GELU if self.act == "quick_gelu" else ops.ACT_GELU)
+        return FN.LinearFn.apply(h, _bf16(self.fc2.weight), _f32(self.fc2.bias), residual, None)
 
     def forward(self, x):
         h = self.fc1(x)
@@ -88,6 +128,9 @@ class _Layer(nn.Module):
         self.layer_norm2 = nn.LayerNorm(cfg.hidden_size, eps=cfg.layer_norm_eps)
 
     def forward(self, x):
+        if x.is_cuda:      # residual adds ride in the out_proj / fc2 GEMM epilogues
+            x = self.self_attn.forward_kernels(_ln_k(self.layer_norm1, x), x)
+            return self.mlp.forward_kernels(_ln_k(self.layer_norm2, x), x)
         x = x + self.self_attn(self.layer_norm1(x))
         return x + self.mlp(self.layer_norm2(x))
 
@@ -124,9 +167,23 @@ class CLIPTextModel(nn.Module):
         with open(os.path.join(d, "config.json")) as f:
             cfg = CLIPTextConfig(**json.load(f))
         m = cls(cfg)
-        for name in ("pytorch_model.bin",):
-            if os.path.exists(os.path.join(d, name)):
-                m.load_state_dict(torch.load(os.path.join(d, name), map_location="cpu"), strict=False)
+        sd = {}
+        for name in ("model.safetensors", "pytorch_model.bin"):
+            f = os.path.join(d, name)
+            if os.path.exists(f):
+                if name.endswith(".safetensors"):
+                    from safetensors.torch import load_file
+                    sd = load_file(f, device="cpu")
+                else:
+                    sd = torch.load(f, map_location="cpu")
+                break
+        if not sd:
+            raise FileNotFoundError(f"no text-encoder weights under {d} (model.safetensors / pytorch_model.bin)")
+        missing, unexpected = m.load_state_dict(sd, strict=False)
+        missing = [k for k in missing if "position_ids" not in k]
+        unexpected = [k for k in unexpected if "position_ids" not in k]
+        if missing or unexpected:
+            raise RuntimeError(f"text encoder checkpoint mismatch: missing {missing[:5]} unexpected {unexpected[:5]}")
         return m
 
     @property
@@ -162,7 +219,15 @@ class CLIPTextModel(nn.Module):
         if input_ids is not None:
             input_ids = input_ids.view(-1, input_ids.shape[-1])
         x = self.text_model.embeddings(input_ids=input_ids, inputs_embeds=inputs_embeds, position_ids=position_ids)
-        x = self.text_model.final_layer_norm(self.text_model.encoder(x))
+        if x.is_cuda:
+            N, D = x.shape[1], x.shape[2]
+            dh = D // self.config.num_attention_heads
+            if N > 128 or dh > 64 or dh % 8 != 0:
+                raise NotImplementedError(f"CLIP text tower on the e4t kernels needs N <= 128 and head dim <= 64 (got {N}, {dh})")
+            out_dtype = x.dtype
+            x = _ln_k(self.text_model.final_layer_norm, self.text_model.encoder(FN.as_bf16(x))).to(out_dtype)
+        else:
+            x = self.text_model.final_layer_norm(self.text_model.encoder(x))
         pooled = x[:, 0]                                                         # modeling_clip.py:72
         if return_dict is False:
             return (x, pooled)

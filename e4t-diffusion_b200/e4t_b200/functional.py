@@ -99,8 +99,35 @@ class LinearFn(torch.autograd.Function):
         if len(ctx.needs_input_grad) > 4 and ctx.needs_input_grad[4] and x2 is not None:
             dw = torch.zeros((N, K), device=dy2.device, dtype=F32)
             ops.gemm(dy2, x2, a_mn=True, b_mn=True, out=dw, accumulate=True, splits=_wgrad_splits(x2.shape[0], N, K))
-            dw = dw.view(ctx.wshape)
+            kw = 1
+            for d in ctx.wshape[1:]:
+                kw *= d
+            dw = (dw if kw == K else dw[:, :kw]).reshape(ctx.wshape)     # operand copies may be K-padded (ViT patch embed)
         return dx, None, db, (dy if ctx.has_res else None), dw
+
+
+class BatchedLinearFn(torch.autograd.Function):
+    """Y[i] = X[i] @ W[i]ᵀ for a stack of independent linears (E4TEncoder's 129 first_linears, encoder.py:159-162, as ONE
+    batched tcgen05 GEMM instead of 129 launches).  x (n,B,K) bf16; w16 (n,N,K) bf16 operand copy of the stacked fp32
+    master `wst`.  Backward: dX (batched GEMM) and dW (n,N,K) fp32 = dY[i]ᵀ X[i] (batched, written once — no atomics)."""
+
+    @staticmethod
+    def forward(ctx, x, w16, wst):
+        x = _c(x)
+        y = ops.gemm(x, w16)
+        ctx.save_for_backward(x, w16)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w16 = ctx.saved_tensors
+        dy = _c(dy)
+        dx = ops.gemm(dy, w16, b_mn=True) if ctx.needs_input_grad[0] else None
+        dw = None
+        if ctx.needs_input_grad[2]:
+            dw = torch.empty(w16.shape, device=dy.device, dtype=F32)
+            ops.gemm(dy, x, a_mn=True, b_mn=True, out=dw)
+        return dx, None, dw
 
 
 class WOLinearFn(torch.autograd.Function):

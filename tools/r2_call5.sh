@@ -9,3 +9,6 @@ for r in json.load(open("gpurun_out/attn_bench.json"))[:2]:
 PY
 E4T_ATTN_FWD2=p0 timeout 120 ncu --set full --import-source on --clock-control none -k regex:attn_fwd2 -c 1 -o gpurun_out/r2c5_fwd2_p0 -f python tools/prof_attn.py > gpurun_out/r2c5_ncu_p0.log 2>&1; echo "ncu rc=$?"
 timeout 600 python -m pytest tests/test_tuning_gpu.py tests/test_dropin_gpu.py -m gpu -q -s --timeout 300 -p no:cacheprovider > gpurun_out/r2c5_tuning.log 2>&1; echo "tuning tests rc=$?"; grep -E "^\[|passed|failed|Error|FAILED|assert" gpurun_out/r2c5_tuning.log | cut -c1-300 | head -40
+timeout 200 python tools/gemm_probe.py > gpurun_out/r2c5_gemm_probe.log 2>&1; echo "gemm_probe rc=$?"; cat gpurun_out/r2c5_gemm_probe.log | cut -c1-260
+timeout 500 python -m pytest tests/test_e2e_gpu.py tests/test_kernels_gpu.py -m gpu -x -q --timeout 400 -p no:cacheprovider > gpurun_out/r2c5_e2e.log 2>&1; echo "e2e+kernels rc=$?"; tail -4 gpurun_out/r2c5_e2e.log | cut -c1-300
+timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-micro > gpurun_out/r2c5_bench.json 2> gpurun_out/r2c5_bench.err; echo "bench rc=$?"; cut -c1-300 gpurun_out/r2c5_bench.json; tail -3 gpurun_out/r2c5_bench.err
