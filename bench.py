@@ -35,7 +35,9 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=16, help="per-GPU batch (BASELINE config: 16)")
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch_stock"],
+                    help="reference = the reference's CPU path on the host cores; torch_stock = the same step in stock torch "
+                         "ops (cuBLAS/cuDNN/SDPA, bf16 autocast) on the GPU: the on-box library comparator")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-micro", action="store_true")
@@ -187,8 +189,8 @@ def micro_rooflines(B, peaks, device):
     o, lse = ops.attn_fwd(q, k, v, H)
     do = torch.randn_like(o)
     t = timeit(lambda: ops.attn_bwd(q, k, v, o, do, lse, H))
-    res["attn_bwd_fused_L0_self"] = dict(ms=t * 1e3, tflops=2.5 * fl / t / 1e12, flops=2.5 * fl,
-                                         note="algorithmic 2.5x fwd (recompute excluded)")
+    res["attn_bwd_fused_L0_self"] = dict(ms=t * 1e3, tflops=2.0 * fl / t / 1e12, flops=2.0 * fl,
+                                         note="SURVEY.md §8d: backward = 2x forward (dQ, dK, dV, dP; the S recompute is not counted)")
     # (2) fused WO-modulated QKV projection GEMM, level 0: (B*4096, 320) x (960, 320)^T
     x = (torch.randn(B * N, C, device=device, generator=g)).to(torch.bfloat16)
     w = (torch.randn(3 * C, C, device=device, generator=g) * 0.05).to(torch.bfloat16)
@@ -211,6 +213,75 @@ def micro_rooflines(B, peaks, device):
     res["groupnorm_silu_320_64"] = dict(ms=t * 1e3, gbs=byts / t / 1e9, frac_hbm=byts / t / 1e9 / peaks["hbm"])
     del flush
     return res
+
+
+def attention_aggregate(B, peaks, device):
+    """SURVEY.md §8d aggregate for the 'fused WeightOffsets-attention' of north_star: WO-modulated QKV projections +
+    attention core, forward and backward, over BOTH UNet passes of a step (759 GFLOP per image per step, out-proj
+    excluded, backward = 2x forward).  Every distinct kernel signature is timed alone (CUDA events, L2 flushed) and
+    weighted by its call count in the step; FLOPs are the analytic figure F = 2·N·Rq·C + 4·M·Rkv·C + 4·N·M·C per module."""
+    from e4t_b200 import ops
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
+
+    def timeit(fn, iters=5):
+        fn(); fn()
+        ts = []
+        for _ in range(iters):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); e1.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        return ts[len(ts) // 2] * 1e-3
+
+    bf = torch.bfloat16
+    levels = [(4096, 320, 5, 2), (1024, 640, 5, 2), (256, 1280, 5, 2), (64, 1280, 1, 1)]   # (N, C, modules full, enc-half)
+    H, Mx, Rx = 8, 77, 768
+    tot_t = tot_f = 0.0
+    rows = []
+    for N, C, n_full, n_enc in levels:
+        cnt = n_full + n_enc
+        x = torch.randn(B, N, C, device=device).to(bf)
+        ctx = torch.randn(B, Mx, Rx, device=device).to(bf)
+        w3 = (torch.randn(3 * C, C, device=device) * 0.05).to(bf)
+        w1 = (torch.randn(C, C, device=device) * 0.05).to(bf)
+        wkv = (torch.randn(2 * C, Rx, device=device) * 0.05).to(bf)
+        x2, c2 = x.view(-1, C), ctx.view(-1, Rx)
+        # ---- self-attention module
+        qkv = ops.gemm(x2, w3).view(B, N, 3 * C)
+        q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+        o, lse = ops.attn_fwd(q, k, v, H)
+        do, dqkv = torch.randn_like(o), torch.randn_like(qkv)
+        dw = torch.zeros(3 * C, C, device=device)
+        t_self = (timeit(lambda: ops.gemm(x2, w3)) + timeit(lambda: ops.attn_fwd(q, k, v, H))
+                  + timeit(lambda: ops.attn_bwd(q, k, v, o, do, lse, H))
+                  + timeit(lambda: ops.gemm(dqkv.view(-1, 3 * C), w3, b_mn=True))
+                  + timeit(lambda: ops.gemm(dqkv.view(-1, 3 * C), x2, a_mn=True, b_mn=True, out=dw, accumulate=True, splits=8)))
+        f_self = 3.0 * B * (2.0 * N * C * 3 * C + 4.0 * N * N * C)
+        # ---- cross-attention module
+        qc = ops.gemm(x2, w1).view(B, N, C)
+        kv = ops.gemm(c2, wkv).view(B, Mx, 2 * C)
+        kc, vc = kv[..., :C], kv[..., C:]
+        oc, lsec = ops.attn_fwd(qc, kc, vc, H)
+        dkv = torch.randn_like(kv)
+        dw1, dwkv = torch.zeros(C, C, device=device), torch.zeros(2 * C, Rx, device=device)
+        t_cross = (timeit(lambda: ops.gemm(x2, w1)) + timeit(lambda: ops.gemm(c2, wkv))
+                   + timeit(lambda: ops.attn_fwd(qc, kc, vc, H)) + timeit(lambda: ops.attn_bwd(qc, kc, vc, oc, do, lsec, H))
+                   + timeit(lambda: ops.gemm(do.view(-1, C), w1, b_mn=True)) + timeit(lambda: ops.gemm(dkv.view(-1, 2 * C), wkv, b_mn=True))
+                   + timeit(lambda: ops.gemm(do.view(-1, C), x2, a_mn=True, b_mn=True, out=dw1, accumulate=True, splits=8))
+                   + timeit(lambda: ops.gemm(dkv.view(-1, 2 * C), c2, a_mn=True, b_mn=True, out=dwkv, accumulate=True, splits=2)))
+        f_cross = 3.0 * B * (2.0 * N * C * C + 4.0 * Mx * Rx * C + 4.0 * N * Mx * C)
+        tot_t += cnt * (t_self + t_cross)
+        tot_f += cnt * (f_self + f_cross)
+        rows.append(dict(N=N, C=C, modules=cnt, self_ms=t_self * 1e3, self_tflops=f_self / t_self / 1e12,
+                         cross_ms=t_cross * 1e3, cross_tflops=f_cross / t_cross / 1e12))
+        del x, ctx, qkv, o, do, dqkv, qc, kv, oc
+    del flush
+    ach = tot_f / tot_t / 1e12
+    return dict(kernels="WO-modulated QKV projection GEMMs + attention core, fwd + bwd, all 32 modules x both UNet passes",
+                gflop_per_image_per_step=tot_f / B / 1e9, ms_per_step=tot_t * 1e3, achieved=ach,
+                peak=peaks["bf16_sustained"], unit="TFLOP/s", frac=ach / peaks["bf16_sustained"],
+                peak_source=peaks["source"] + ", sustained figure (kernels run inside a long step)", by_level=rows)
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -266,28 +337,74 @@ def run_reference(args):
         return
     state = cpu_oracle_setup()
     cores = torch.get_num_threads()
-    B = 1
-    t_w, _ = cpu_oracle_step(state, B, 1)                     # warm-up (also sizes the run)
-    budget = 200.0
-    steps = max(1, min(args.steps, int(budget // max(t_w, 1e-3))))
+    B = 2                                                      # BASELINE.json configs[0]: bs=2, 10 steps, CPU fp32
+    t_w, _ = cpu_oracle_step(state, B, 1)                      # 1 warm-up step (also sizes the run)
+    budget = 240.0
+    want = 10 if args.steps <= 0 else min(args.steps, 10)
+    steps = max(1, min(want, int(budget // max(t_w, 1e-3))))
     ts = []
     for i in range(steps):
         t, _ = cpu_oracle_step(state, B, 2 + i)
         ts.append(t)
     tot = sum(ts)
     val = B * steps / tot
-    sample = (f"{steps} timed step(s) (of {args.steps} requested; capped to ~{int(budget)} s of CPU work) of the full "
-              f"pre-training step at B={B} image/step, SD-v1.4 UNet + ViT-H/14 + CLIP-L text, fp32, "
-              f"torch.set_num_threads({cores}) of {os.cpu_count()} host cores; 1 warm-up step")
+    sample = (f"BASELINE configs[0] (bs=2, 10 steps, CPU fp32): {steps} timed step(s) after 1 warm-up"
+              f"{'' if steps == 10 else ' (capped to ~%d s of CPU work)' % int(budget)} of the full pre-training step, "
+              f"SD-v1.4 UNet + ViT-H/14 + CLIP-L text, torch.set_num_threads({cores}) of {os.cpu_count()} host cores")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "images/sec", "n_gpus": args.gpus,
             "steps": steps, "warmup": 1, "ms_per_step": tot / steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "SD-v1.4 E4T pretrain step, random-init, 512^2 (CPU oracle port of the reference path)",
-                       "per_step_batch": B, "device": "host CPU"},
+                       "per_step_batch": B, "device": "host CPU", "same_model_as_gpu_arm": True},
             "cpu_baseline": {"value": val, "unit": "images/sec", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
+
+
+def run_torch_stock(args):
+    """--impl torch_stock: the SAME step expressed in stock torch ops on the GPU (F.conv2d / F.linear -> cuDNN / cuBLAS,
+    F.scaled_dot_product_attention, torch autograd, torch.optim.AdamW(fused), bf16 autocast, fp32 masters): what the
+    reference's modules would launch on this B200.  Comparator only — never on the product path."""
+    from oracle import e4t_oracle as O
+    assert torch.cuda.is_available()
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    O.USE_SDPA = True
+    state = cpu_oracle_setup()
+    _, sd_u, sd_e, sd_t, _ = state
+    for sd in (sd_u, sd_e, sd_t):
+        for k in list(sd):
+            rg = sd[k].requires_grad
+            sd[k] = sd[k].detach().to(dev).requires_grad_(rg)
+    train = [v for v in list(sd_u.values()) + list(sd_e.values()) if v.requires_grad]
+    opt = torch.optim.AdamW(train, lr=1.6e-5, fused=True)
+    B = args.batch
+    batches = [{k: v.to(dev) for k, v in O.synth_batch(B, 42 + i).items()} for i in range(2)]
+
+    def one(b):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = O.pretrain_step(sd_u, O.SD14_UNET, sd_e, O.VIT_H14, sd_t, O.CLIP_TEXT_L, b)
+        opt.zero_grad(set_to_none=True)
+        out["loss"].backward()
+        opt.step()
+        return out["loss"]
+    for i in range(max(args.warmup, 1)):
+        one(batches[i % 2])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        loss = one(batches[i % 2])
+    e1.record()
+    torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) * 1e-3
+    print(json.dumps({"impl": "torch_stock", "metric": METRIC, "value": B * args.steps / t, "unit": "images/sec",
+                      "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t / args.steps * 1e3,
+                      "higher_is_better": True, "dtype": "bf16 autocast", "data": "synthetic", "loss": float(loss),
+                      "config": {"workload": "same step in stock torch ops (cuBLAS/cuDNN/SDPA), eager, all base-weight "
+                                             "gradients skipped like our arm (only wo + encoder head require grad)",
+                                 "per_gpu_batch": B}}))
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -295,6 +412,9 @@ def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+        return
+    if args.impl == "torch_stock":
+        run_torch_stock(args)
         return
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -396,23 +516,32 @@ def main():
         torch.cuda.empty_cache()
         micro = micro_rooflines(B, peaks, device)
         a = micro["attn_fwd_L0_self"]
-        roof = {"kernel": "attn_fwd_kernel (level-0 self-attention core, N=M=4096, 8x40, B=%d)" % B,
+        traffic, traffic_src = None, None
+        try:   # dram__bytes_read.sum + dram__bytes_write.sum of the SHIPPED kernel from its ncu --set full capture
+            with open(os.path.join(ROOT, "profiles", "r02_attn_fwd_ncu.json")) as f:
+                tj = json.load(f)
+            if B == tj.get("batch"):
+                traffic, traffic_src = tj["dram_bytes_read"] + tj["dram_bytes_write"], tj["source"]
+        except Exception:
+            pass
+        roof = {"kernel": "attention forward core (attn_fwd2_kernel; level-0 self-attention, N=M=4096, 8x40, B=%d)" % B,
                 "bound": "tensor", "achieved": a["tflops"], "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
-                "frac": a["tflops"] / peaks["bf16_burst"],
-                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape from the ncu --set full
-                # capture summarised in profiles/r01_ncu_full_summary.md (algorithmic: Q,K,V read + O write = 168 MB)
-                "traffic": 152436224 if B == 16 else None,
-                "algorithmic_flops_per_launch": a["flops"], "peak_source": peaks["source"] + ", burst figure "
-                "(kernel timed alone, L2 flushed between launches)"}
+                "frac": a["tflops"] / peaks["bf16_burst"], "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_flops_per_launch": a["flops"],
+                "algorithmic_bytes_per_launch": 4 * B * 4096 * 320 * 2,
+                "peak_source": peaks["source"] + ", burst figure (kernel timed alone, L2 flushed between launches)",
+                "aggregate_wo_attention": attention_aggregate(B, peaks, device)}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             state = cpu_oracle_setup()
-            t_cpu, _ = cpu_oracle_step(state, 1, 1)
-            cpu = {"value": 1.0 / t_cpu, "unit": "images/sec", "cores": torch.get_num_threads(), "kind": "port",
-                   "sample": "ONE full pre-training step at B=1 image (SD-v1.4 UNet x2 fwd + ViT-H/14 + CLIP-L text + "
-                             "bwd + AdamW), fp32 CPU oracle (oracle/e4t_oracle.py), all host threads, no warm-up"}
+            cpu_oracle_step(state, 2, 1)                       # warm-up
+            t_cpu, _ = cpu_oracle_step(state, 2, 2)
+            cpu = {"value": 2.0 / t_cpu, "unit": "images/sec", "cores": torch.get_num_threads(), "kind": "port",
+                   "sample": "ONE timed full pre-training step after one warm-up step at B=2 images (BASELINE configs[0] "
+                             "batch; SD-v1.4 UNet x2 fwd + ViT-H/14 + CLIP-L text + bwd + AdamW), fp32 CPU oracle "
+                             "(oracle/e4t_oracle.py), torch threads = min(host cores, 32)"}
             del state
         except Exception as ex:  # the baseline must never take the GPU number down with it
             cpu = {"value": None, "unit": "images/sec", "cores": os.cpu_count(), "kind": "port",

@@ -239,7 +239,13 @@ class E4TEncoder(ModelMixin, ConfigMixin):
         x = (x + 1.0) / 2.0
         return (x - self.mean.view(1, 3, 1, 1)) / self.std.view(1, 3, 1, 1)
 
-    def forward(self, x, unet_down_block_samples: tuple):
+    def image_features(self, x):
+        """(pooled, tokens) of the conditioning image: step-invariant in the sampling loop, where the pipeline computes
+        them once per call and passes them back through forward(clip_features=...)."""
+        with torch.no_grad():
+            return self.clip_vision(self.preprocess(x))
+
+    def forward(self, x, unet_down_block_samples: tuple, clip_features=None):
         maps = []
         for m in unet_down_block_samples:
             if m.dim() == 4 and m.is_cuda and m.dtype == torch.bfloat16 and m.permute(0, 2, 3, 1).is_contiguous():
@@ -255,7 +261,7 @@ class E4TEncoder(ModelMixin, ConfigMixin):
         fe0, fe2 = self.unet_feature_embedder[0], self.unet_feature_embedder[2]
         u = FN.LinearFn.apply(u.to(bf), _bf16(fe0.weight), fe0.bias, None, fe0.weight)               # :149  (B,W)
         u = FN.LinearFn.apply(FN.ActFn.apply(u, ops.ACT_LEAKY_RELU), _bf16(fe2.weight), fe2.bias, None, fe2.weight)
-        pooled, tokens = self.clip_vision(self.preprocess(x))                                    # :153-154
+        pooled, tokens = clip_features if clip_features is not None else self.clip_vision(self.preprocess(x))  # :153-154
         hs = torch.cat([pooled.unsqueeze(1), tokens[:, 1::2, :]], dim=1)                         # :155-156  (B,n,W)
         B, n, W = hs.shape
         if n != len(self.first_linears):

@@ -265,6 +265,9 @@ def wo_delta_closed_form(sd, p):
     return b[:, None] * a[None, :] + s[:, None] * bc[None, :] + br[:, None]
 
 
+USE_SDPA = False
+
+
 def cross_attention(sd, p, x, ctx, heads):
     """CrossAttnProcessor.__call__ (cross_attention.py:285-322) == AttnProcessor2_0 (:490-538) numerically."""
     ctx = x if ctx is None else ctx
@@ -276,8 +279,11 @@ def cross_attention(sd, p, x, ctx, heads):
     q = q.view(B, N, heads, dh).transpose(1, 2)
     k = k.view(B, -1, heads, dh).transpose(1, 2)
     v = v.view(B, -1, heads, dh).transpose(1, 2)
-    s = (q @ k.transpose(-1, -2)) * dh ** -0.5                                     # scale = dim_head**-0.5 (:59)
-    o = (s.softmax(-1) @ v).transpose(1, 2).reshape(B, N, C)
+    if USE_SDPA:   # AttnProcessor2_0 literally (:527-529); used by bench.py's on-GPU stock-torch comparator
+        o = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(B, N, C)
+    else:
+        s = (q @ k.transpose(-1, -2)) * dh ** -0.5                                 # scale = dim_head**-0.5 (:59)
+        o = (s.softmax(-1) @ v).transpose(1, 2).reshape(B, N, C)
     return F.linear(o, sd[p + "to_out.0.weight"], sd[p + "to_out.0.bias"])        # :534
 
 
@@ -320,7 +326,7 @@ def resnet_block(sd, p, x, temb, groups, eps):
 def timestep_embedding(t, dim, flip_sin_to_cos=True, freq_shift=0):
     """diffusers 0.14.0 get_timestep_embedding (restated)."""
     half = dim // 2
-    exponent = -math.log(10000) * torch.arange(half, dtype=torch.float32) / (half - freq_shift)
+    exponent = -math.log(10000) * torch.arange(half, dtype=torch.float32, device=t.device) / (half - freq_shift)
     emb = t[:, None].float() * torch.exp(exponent)[None, :]
     emb = torch.cat([torch.sin(emb), torch.cos(emb)], dim=-1)
     if flip_sin_to_cos:
@@ -387,7 +393,7 @@ def _mha(x, w_in, b_in, w_out, b_out, heads, causal=False):
     q, k, v = (t.view(B, N, heads, dh).transpose(1, 2) for t in (q, k, v))
     s = (q @ k.transpose(-1, -2)) * dh ** -0.5
     if causal:
-        s = s + torch.full((N, N), float("-inf"), dtype=s.dtype).triu(1)
+        s = s + torch.full((N, N), float("-inf"), dtype=s.dtype, device=s.device).triu(1)
     return F.linear((s.softmax(-1) @ v).transpose(1, 2).reshape(B, N, W), w_out, b_out)
 
 
@@ -396,7 +402,7 @@ def vit_forward(sd, v, x, p="clip_vision.", ln_post_on_tokens=False):
     W = v["width"]
     x = F.conv2d(x, sd[p + "conv1.weight"], stride=v["patch"])
     x = x.reshape(x.shape[0], W, -1).permute(0, 2, 1)
-    cls = sd[p + "class_embedding"].to(x.dtype) + torch.zeros(x.shape[0], 1, W, dtype=x.dtype)
+    cls = sd[p + "class_embedding"].to(x.dtype) + torch.zeros(x.shape[0], 1, W, dtype=x.dtype, device=x.device)
     x = torch.cat([cls, x], dim=1) + sd[p + "positional_embedding"]
     x = F.layer_norm(x, (W,), sd[p + "ln_pre.weight"], sd[p + "ln_pre.bias"], 1e-5)
     for i in range(v["layers"]):
@@ -418,8 +424,8 @@ def encoder_preprocess(x, image_size=224):
     """encoder.py:131-139 (kornia bicubic resize, align_corners=True, no antialias; then CLIP normalisation)."""
     x = F.interpolate(x, size=(image_size, image_size), mode="bicubic", align_corners=True)
     x = (x + 1.0) / 2.0
-    mean = torch.tensor(CLIP_MEAN, dtype=x.dtype).view(1, 3, 1, 1)
-    std = torch.tensor(CLIP_STD, dtype=x.dtype).view(1, 3, 1, 1)
+    mean = torch.tensor(CLIP_MEAN, dtype=x.dtype, device=x.device).view(1, 3, 1, 1)
+    std = torch.tensor(CLIP_STD, dtype=x.dtype, device=x.device).view(1, 3, 1, 1)
     return (x - mean) / std
 
 
@@ -492,7 +498,7 @@ def ddpm_alphas_cumprod(n=1000, beta_start=0.00085, beta_end=0.012):
 
 
 def add_noise(latents, noise, timesteps, acp=None):
-    acp = ddpm_alphas_cumprod() if acp is None else acp
+    acp = (ddpm_alphas_cumprod() if acp is None else acp).to(latents.device)
     a = acp[timesteps].to(latents.dtype) ** 0.5
     s = (1 - acp[timesteps].to(latents.dtype)) ** 0.5
     return a.view(-1, 1, 1, 1) * latents + s.view(-1, 1, 1, 1) * noise                               # :621
@@ -506,7 +512,7 @@ def pretrain_step(sd_unet, ucfg, sd_enc, vcfg, sd_text, tcfg, batch, class_token
     B = latents.shape[0]
     emb_w = sd_text["text_model.embeddings.token_embedding.weight"]
     class_embed = emb_w[class_token_id].detach()                                                      # :561-564
-    ids_e4t = torch.tensor([[BOS] + [EOS] * 76], dtype=torch.int64)
+    ids_e4t = torch.tensor([[BOS] + [EOS] * 76], dtype=torch.int64, device=latents.device)
     with torch.no_grad():
         ehs_e4t = text_forward(sd_text, tcfg, input_ids=ids_e4t)                                      # :565-583
     inputs_embeds = emb_w[input_ids].detach().clone()                                                 # :616
@@ -550,3 +556,50 @@ def golden_unet_inputs(cfg, B, seed, hw, enc_shapes=None):
     w = torch.randn(B, 4, hw, hw, generator=g)
     wenc = [torch.randn(tuple(s), generator=g) for s in enc_shapes] if enc_shapes is not None else None
     return x, t, ehs, w, wenc
+
+
+# ------------------------------------------------------------------------------------------------
+# inference: StableDiffusionE4TPipeline.__call__ (e4t/pipeline_stable_diffusion_e4t.py:91-250) with the SD-v1.x DDIM
+# scheduler of diffusers 0.14.0 (restated: scaled-linear betas, steps_offset 1, clip_sample False, set_alpha_to_one False)
+# ------------------------------------------------------------------------------------------------
+def ddim_timesteps(num_inference_steps, num_train=1000, steps_offset=1):
+    ratio = num_train // num_inference_steps
+    return ((torch.arange(0, num_inference_steps) * ratio).round().flip(0).to(torch.int64) + steps_offset).tolist()
+
+
+def ddim_step(eps, t, x, num_inference_steps, acp=None, num_train=1000):
+    acp = ddpm_alphas_cumprod() if acp is None else acp
+    prev_t = t - num_train // num_inference_steps
+    a_t = acp[t]
+    a_prev = acp[prev_t] if prev_t >= 0 else acp[0]
+    pred_x0 = (x - (1 - a_t) ** 0.5 * eps) / a_t ** 0.5
+    return a_prev ** 0.5 * pred_x0 + (1 - a_prev) ** 0.5 * eps
+
+
+def pipeline_sample(sd_unet, ucfg, sd_enc, vcfg, sd_text, tcfg, image, input_ids, latents, num_inference_steps=4,
+                    guidance_scale=7.5, class_token_id=320, domain_embed_scale=0.1):
+    """The denoising loop of pipeline_stable_diffusion_e4t.py:181-216 on explicit prompt ids / starting latents."""
+    emb_w = sd_text["text_model.embeddings.token_embedding.weight"]
+    bsz = latents.shape[0]
+    idx = input_ids[0].tolist().index(PLACEHOLDER_ID)                                                  # :77
+    with torch.no_grad():
+        ehs_e4t = text_forward(sd_text, tcfg, input_ids=torch.tensor([[BOS] + [EOS] * 76])).expand(bsz, -1, -1)
+        base_embeds = emb_w[input_ids]
+        class_embed = emb_w[class_token_id]
+        pix = image.expand(bsz, -1, -1, -1)
+        x = latents.clone()
+        for t in ddim_timesteps(num_inference_steps):
+            tt = torch.full((bsz,), t, dtype=torch.int64)
+            enc = unet_forward(sd_unet, ucfg, x, tt, ehs_e4t, return_encoder_outputs=True)             # :191
+            dom = class_embed.expand(bsz, -1) + domain_embed_scale * encoder_forward(sd_enc, vcfg, pix, enc["down_block_samples"])
+            emb = base_embeds.expand(bsz, -1, -1).clone()
+            emb[:, idx, :] = dom                                                                       # :197-198
+            ehs = text_forward(sd_text, tcfg, inputs_embeds=emb)                                       # :200
+            if guidance_scale > 1.0:
+                eps = unet_forward(sd_unet, ucfg, torch.cat([x, x]), torch.cat([tt, tt]), torch.cat([ehs_e4t, ehs]))
+                u, c = eps.chunk(2)
+                eps = u + guidance_scale * (c - u)                                                     # :211-213
+            else:
+                eps = unet_forward(sd_unet, ucfg, x, tt, ehs)
+            x = ddim_step(eps, t, x, num_inference_steps)                                              # :216
+    return x

@@ -12,3 +12,5 @@ timeout 600 python -m pytest tests/test_tuning_gpu.py tests/test_dropin_gpu.py -
 timeout 200 python tools/gemm_probe.py > gpurun_out/r2c5_gemm_probe.log 2>&1; echo "gemm_probe rc=$?"; cat gpurun_out/r2c5_gemm_probe.log | cut -c1-260
 timeout 500 python -m pytest tests/test_e2e_gpu.py tests/test_kernels_gpu.py -m gpu -x -q --timeout 400 -p no:cacheprovider > gpurun_out/r2c5_e2e.log 2>&1; echo "e2e+kernels rc=$?"; tail -4 gpurun_out/r2c5_e2e.log | cut -c1-300
 timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-micro > gpurun_out/r2c5_bench.json 2> gpurun_out/r2c5_bench.err; echo "bench rc=$?"; cut -c1-300 gpurun_out/r2c5_bench.json; tail -3 gpurun_out/r2c5_bench.err
+timeout 300 python -m pytest tests/test_pipeline_gpu.py -m gpu -q -s --timeout 200 -p no:cacheprovider > gpurun_out/r2c5_pipeline.log 2>&1; echo "pipeline rc=$?"; grep -E "^\[|passed|failed|Error" gpurun_out/r2c5_pipeline.log | cut -c1-300
+timeout 120 ncu --set full --import-source on --clock-control none -k regex:gn_ -s 8 -c 8 -o gpurun_out/r2c5_gn -f python tools/prof_gn.py > gpurun_out/r2c5_ncu_gn.log 2>&1; echo "ncu gn rc=$?"
