@@ -5,18 +5,24 @@
 // block needs 16384 exponentials but only ~390 clk of tensor-core time: the kernel is bound by the softmax threads, not
 // by the MMAs.  attn_fwd_kernel (attention.cu) covered the tensor-core/softmax hand-off latency with two CTAs per SM and
 // 16 narrow softmax warps that exchange row maxima through shared memory; ncu showed 26 % of its samples spinning on
-// the S-ready barrier and 17 % in idle role warps.  Here ONE CTA per SM owns TWO 128-query tiles:
+// the S-ready barrier and 17 % in idle role warps.  Here ONE CTA per SM owns NT 128-query tiles:
 //
-//   warp 0        TMA producer   Q0,Q1 once; K_j / V_j ring (kst stages)
-//   warp 1        MMA issuer     S_t = Q_t K_j^T  and  O_t += P_t V_j  for t = 0,1, interleaved so that the tensor core
-//                                works on tile t while the softmax warps of tile 1-t are busy
-//   warps 4-7     softmax tile 0 one query row per THREAD (TMEM lane == row): the whole 128-wide score row sits in
-//   warps 8-11    softmax tile 1 registers, so there is no cross-thread max exchange, no named barrier, no shuffle
+//   warp 0            TMA producer   Q_0..Q_{NT-1} once; K_j / V_j ring (kst stages of BKV keys)
+//   warp 1            MMA issuer     S_t = Q_t K_j^T  and  O_t += P_t V_j  for t = 0..NT-1, interleaved so that the tensor
+//                                    core works on tile t while the softmax warps of the other tiles are busy
+//   warps 4+4t..7+4t  softmax tile t one query row per THREAD (TMEM lane == row): the whole BKV-wide score row sits in
+//                                    registers, so there is no cross-thread max exchange, no shuffle
 //
-//   TMEM  S0 [0,128) | S1 [128,256) | O0 [256, 256+dpad) | O1 [.., 256+2 dpad)       (dh <= 128)
-//         P_t (bf16, two per 32-bit column) overwrites columns [0,64) of S_t and is consumed by O_t += P_t V_j as the
-//         TMEM A operand (tcgen05.mma [d], [a], bdesc): P never touches shared memory.  The tensor pipe executes in
+//   TMEM  S_t [t BKV, (t+1) BKV) | O_t [NT BKV + t dpad, ..)                       NT (BKV + dpad) <= 512
+//         P_t (bf16, two per 32-bit column) overwrites columns [0, BKV/2) of S_t and is consumed by O_t += P_t V_j as
+//         the TMEM A operand (tcgen05.mma [d], [a], bdesc): P never touches shared memory.  The tensor pipe executes in
 //         issue order, so S_t(j+1) = Q_t K_{j+1}^T, issued after P_t(j) V_j, cannot overwrite P_t(j) early.
+//
+//   Two shapes are instantiated.  <NT 2, BKV 128> (12 warps, 168 registers): two warps per SM sub-partition; ncu (r02)
+//   showed that ONE warp per sub-partition cannot keep the MUFU pipe busy in an in-order issue stream (61 % inside the
+//   exponential phase: every fixed-latency dependency is exposed), and two warps that run in lock-step both wait 31 % of
+//   the time for the tensor core.  <NT 4, BKV 64> (20 warps, 96 registers, head dim <= 64) keeps FOUR row-private warps
+//   per sub-partition in flight at different phases of different tiles.
 //
 // Softmax details
 //   * lazy rescale with a threshold: the running reference max m only moves when a block's max exceeds it by more than
@@ -95,25 +101,18 @@ __device__ __forceinline__ u64 exp2_poly2(u64 x2) {
 }
 
 // POLY8: pairs (of every 8 consecutive pairs) whose exp2 runs on the FMA pipe; 0 = all on MUFU.
-// BF16X: exponentials by ex2.approx.ftz.bf16x2 — ONE MUFU operation per PAIR of scores (measured on B200,
-//        tools/micro/pipe_rates.cu: 0.5 warp-instructions/clk/SM for the f32, f16x2 and bf16x2 forms alike, so the packed
-//        forms double the exponential rate to 32/clk/SM); the result is already the bf16 pair the P·V MMA consumes.
-//        (An fp16 P against a bf16 V is not an option: tcgen05.mma kind::f16 with a_format != b_format raises an
-//        illegal-instruction error on sm_100a — tried in round 2.)  The price is that the ARGUMENT (s - m)·scale·log2e
-//        is rounded to bf16 before the exponential: relative error of p <= 0.00135·|x|, i.e. below the 2^-9 rounding
-//        of p itself for |x| < 1.4 and growing only where p has already decayed by 2^-|x|.
-// The MUFU instructions are `asm volatile`: plain asm let the compiler hoist the whole exponential phase above the
-// exp-phase token barrier (ncu r02: both warpgroups then ran in lock-step and waited 31 % of the time for S).
-template <int POLY8, bool BF16X>
-__global__ void __launch_bounds__(384, 1)
+template <int NT, int BKV, int POLY8>
+__global__ void __launch_bounds__(128 + 128 * NT, 1)
 attn_fwd2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                  const __grid_constant__ CUtensorMap mapV, const AttnArgs a) {
+  constexpr int NP = BKV / 2;                     // score pairs per row and block (= 32-bit P columns)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int q_bytes = a.DC * 16384;             // one 128-query tile
-  const int kv_tile = a.DC * 128 * 128;         // one 128-key block of K (or V)
-  uint8_t* sQ = smem;                           // [2 tiles][DC][128][64]
-  uint8_t* sK = sQ + 2 * q_bytes;               // [kst][DC][128][64]
+  const int q_bytes = a.DC * 16384;               // one 128-query tile
+  const int kv_chunk = BKV * 128;                 // one 64-wide d chunk of a BKV-key block
+  const int kv_tile = a.DC * kv_chunk;
+  uint8_t* sQ = smem;                             // [NT tiles][DC][128][64]
+  uint8_t* sK = sQ + NT * q_bytes;                // [kst][DC][BKV][64]
   uint8_t* sV = sK + a.kst * kv_tile;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sV + a.kst * kv_tile);
   uint64_t* q_full = bars;            // [1]
@@ -121,14 +120,14 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
   uint64_t* k_empty = k_full + 4;     // [4]
   uint64_t* v_full = k_empty + 4;     // [4]
   uint64_t* v_empty = v_full + 4;     // [4]
-  uint64_t* s_full = v_empty + 4;     // [2]  MMA -> softmax t : S_t(j) complete (and everything issued before it)
-  uint64_t* p_ready = s_full + 2;     // [2]  softmax t -> MMA : P_t(j) written, O_t rescaled
-  uint64_t* o_done = p_ready + 2;     // [2]  MMA -> softmax t : last P_t V retired
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
+  uint64_t* s_full = v_empty + 4;     // [NT]  MMA -> softmax t : S_t(j) complete (and everything issued before it)
+  uint64_t* p_ready = s_full + NT;    // [NT]  softmax t -> MMA : P_t(j) written, O_t rescaled
+  uint64_t* o_done = p_ready + NT;    // [NT]  MMA -> softmax t : last P_t V retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + NT);
   float* s_zero = reinterpret_cast<float*>(tmem_slot + 2);   // 0.0f: read after the exp-phase token (ordering anchor)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 256, h = blockIdx.y, b = blockIdx.z;
+  const int q0 = blockIdx.x * (128 * NT), h = blockIdx.y, b = blockIdx.z;
 
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);
@@ -138,7 +137,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < NT; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&p_ready[i], 128);
       mbar_init(&o_done[i], 1);
@@ -156,13 +155,13 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tO0 = tmem + 256u;
+  const uint32_t tO0 = tmem + (uint32_t)(NT * BKV);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
-      mbar_expect_tx(q_full, (uint32_t)(2 * q_bytes));
-      for (int t = 0; t < 2; ++t)
+      mbar_expect_tx(q_full, (uint32_t)(NT * q_bytes));
+      for (int t = 0; t < NT; ++t)
         for (int c = 0; c < a.DC; ++c) tma_load_4d(sQ + t * q_bytes + c * 16384, &mapQ, q_full, c * 64, h, q0 + 128 * t, b);
     }
     for (int j = 0; j < a.nblk; ++j) {
@@ -172,34 +171,35 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
       if (elect_one()) {
         mbar_expect_tx(&k_full[st], (uint32_t)kv_tile);
         for (int c = 0; c < a.DC; ++c)
-          tma_load_4d(sK + st * kv_tile + c * 16384, &mapK, &k_full[st], c * 64, h, j * 128, b);
+          tma_load_4d(sK + st * kv_tile + c * kv_chunk, &mapK, &k_full[st], c * 64, h, j * BKV, b);
       }
       mbar_wait(&v_empty[st], ph ^ 1u);
       if (elect_one()) {
         mbar_expect_tx(&v_full[st], (uint32_t)kv_tile);
         for (int c = 0; c < a.DC; ++c)
-          tma_load_4d(sV + st * kv_tile + c * 16384, &mapV, &v_full[st], c * 64, h, j * 128, b);
+          tma_load_4d(sV + st * kv_tile + c * kv_chunk, &mapV, &v_full[st], c * 64, h, j * BKV, b);
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    const uint32_t idesc_s = umma_idesc_bf16(128u, false, false);
+    const uint32_t idesc_s = umma_idesc_bf16((uint32_t)BKV, false, false);
     const uint32_t idesc_o = umma_idesc_bf16((uint32_t)a.dpad, false, true);
     mbar_wait(q_full, 0);
     mbar_wait(&k_full[0], 0);
     tc_fence_after();
     if (elect_one()) {
-      mma_kmajor(tmem, smem_u32(sQ), 16384, smem_u32(sK), 16384, a.dh, a.DC, idesc_s);
-      umma_commit(&s_full[0]);
-      mma_kmajor(tmem + 128u, smem_u32(sQ + q_bytes), 16384, smem_u32(sK), 16384, a.dh, a.DC, idesc_s);
-      umma_commit(&k_empty[0]);
-      umma_commit(&s_full[1]);
+      for (int t = 0; t < NT; ++t) {
+        mma_kmajor(tmem + (uint32_t)(t * BKV), smem_u32(sQ + t * q_bytes), 16384, smem_u32(sK), kv_chunk, a.dh, a.DC,
+                   idesc_s);
+        if (t == NT - 1) umma_commit(&k_empty[0]);
+        umma_commit(&s_full[t]);
+      }
     }
     for (int j = 0; j < a.nblk; ++j) {
       const int st = j % a.kst;
       const int jn = j + 1, stn = jn % a.kst;
       const bool more = jn < a.nblk;
-      for (int t = 0; t < 2; ++t) {
+      for (int t = 0; t < NT; ++t) {
         mbar_wait(&p_ready[t], (uint32_t)(j & 1));
         if (t == 0) {
           mbar_wait(&v_full[st], (uint32_t)((j / a.kst) & 1));
@@ -207,12 +207,12 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
         }
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t tS = tmem + (uint32_t)t * 128u;
-          mma_pv_ts(tO0 + (uint32_t)(t * a.dpad), tS, smem_u32(sV + st * kv_tile), 16384, 128, idesc_o, j > 0 ? 1u : 0u);
-          if (t == 1) umma_commit(&v_empty[st]);
+          const uint32_t tS = tmem + (uint32_t)(t * BKV);
+          mma_pv_ts(tO0 + (uint32_t)(t * a.dpad), tS, smem_u32(sV + st * kv_tile), kv_chunk, BKV, idesc_o, j > 0 ? 1u : 0u);
+          if (t == NT - 1) umma_commit(&v_empty[st]);
           if (more) {
-            mma_kmajor(tS, smem_u32(sQ + t * q_bytes), 16384, smem_u32(sK + stn * kv_tile), 16384, a.dh, a.DC, idesc_s);
-            if (t == 1) umma_commit(&k_empty[stn]);
+            mma_kmajor(tS, smem_u32(sQ + t * q_bytes), 16384, smem_u32(sK + stn * kv_tile), kv_chunk, a.dh, a.DC, idesc_s);
+            if (t == NT - 1) umma_commit(&k_empty[stn]);
             umma_commit(&s_full[t]);
           } else {
             umma_commit(&o_done[t]);
@@ -227,32 +227,31 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
     const int ew = warp & 3;                       // TMEM lane quadrant this warp may access
     const int row = ew * 32 + lane;
     const uint32_t lane_base = (uint32_t)(ew * 32) << 16;
-    const uint32_t tS = tmem + (uint32_t)t * 128u + lane_base;
+    const uint32_t tS = tmem + (uint32_t)(t * BKV) + lane_base;
     const uint32_t tO = tO0 + (uint32_t)(t * a.dpad) + lane_base;
     const float sl2 = a.scale * kLog2e;
     const u64 sl2_2 = f2_pack(sl2, sl2);
     const int ochunk = a.dpad >> 4;
+    const bool token = (NT == 2) && a.pbuf;
     float m = -INFINITY;                           // reference max of this row (raw score units)
     float l0 = 0.f, l1 = 0.f;
-    if (a.pbuf && t == 1) asm volatile("bar.arrive 2, 256;" ::: "memory");   // tile 0 owns the first exp phase
+    if (token && t == 1) asm volatile("bar.arrive 2, 256;" ::: "memory");   // tile 0 owns the first exp phase
     for (int j = 0; j < a.nblk; ++j) {
       mbar_wait(&s_full[t], (uint32_t)(j & 1));
       tc_fence_after();
-      uint32_t v[128];
-      tmem_ld32(tS, v);
-      tmem_ld32(tS + 32u, v + 32);
-      tmem_ld32(tS + 64u, v + 64);
-      tmem_ld32(tS + 96u, v + 96);
-      tmem_ld_wait();
-      const int kv0 = j * 128;
-      if (kv0 + 128 > a.M) {                       // ragged last block: keys >= M are masked out
+      uint32_t v[BKV];
 #pragma unroll
-        for (int e = 0; e < 128; ++e)
+      for (int c = 0; c < BKV; c += 32) tmem_ld32(tS + (uint32_t)c, v + c);
+      tmem_ld_wait();
+      const int kv0 = j * BKV;
+      if (kv0 + BKV > a.M) {                       // ragged last block: keys >= M are masked out
+#pragma unroll
+        for (int e = 0; e < BKV; ++e)
           if (kv0 + e >= a.M) v[e] = 0xff800000u;  // -inf
       }
       float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-      for (int e = 0; e < 128; e += 4) {
+      for (int e = 0; e < BKV; e += 4) {
         mx0 = max3(mx0, __uint_as_float(v[e]), __uint_as_float(v[e + 1]));
         mx1 = max3(mx1, __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
       }
@@ -277,12 +276,10 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
         }
       }
       float nmb = -m * sl2;
-      // exp-phase token: the two softmax warpgroups take turns on the MUFU pipe, so that the tensor-core work of tile t
-      // (P_t V, then S_t of the next block) always runs under the exponentials of tile 1-t instead of both
-      // warpgroups finishing together and then both waiting for the tensor core.  ptxas is free to move pure
-      // register arithmetic across a bar.sync, so the whole exponential phase is made to depend on a (zero) value
+      // exp-phase token (NT == 2 only): the two softmax warpgroups take turns on the MUFU pipe.  ptxas is free to move
+      // pure register arithmetic across a bar.sync, so the exponential phase is made to depend on a (zero) value
       // loaded from shared memory AFTER the barrier.
-      if (a.pbuf) {
+      if (token) {
         if (t == 0) asm volatile("bar.sync 2, 256;" ::: "memory");
         else asm volatile("bar.sync 3, 256;" ::: "memory");
         float z;
@@ -292,52 +289,40 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
       const u64 nmb2 = f2_pack(nmb, nmb);
       u64 ls = f2_pack(0.f, 0.f), ls2 = f2_pack(0.f, 0.f);
       // Software-pipelined by hand (the SM issues in order): the MUFU results of pair e are consumed (row sum, bf16
-      // pack) kLag pairs later, and the scale-and-subtract FFMA2 of pair e + kLead is issued in between, so that no
-      // instruction waits on the ~20-clk MUFU latency of the instruction just before it.  (ncu r02: with
-      // produce-then-consume order the exponential phase of one warp took 1670 clk against 1024 clk of MUFU time.)
+      // pack) kLag pairs later, and the scale-and-subtract FFMA2 of pair e + kLead is issued in between.
       constexpr int kLag = 6, kLead = 4;
-      if constexpr (BF16X || POLY8 != 0) {
+      if constexpr (POLY8 != 0) {
 #pragma unroll
-        for (int e = 0; e < 64; ++e) {               // pair e = columns 2e, 2e+1 (variants kept for measurements)
+        for (int e = 0; e < NP; ++e) {               // pair e = columns 2e, 2e+1
           const u64 x2 = f2_fma(f2_pack(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1])), sl2_2, nmb2);
           u64 p2;
-          if constexpr (BF16X) {
-            float x0, x1;
-            f2_unpack(x2, x0, x1);
-            uint32_t hx, he;
-            asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hx) : "f"(x1), "f"(x0));
-            asm volatile("ex2.approx.ftz.bf16x2 %0, %1;" : "=r"(he) : "r"(hx));
-            p2 = f2_pack(__uint_as_float(he << 16), __uint_as_float(he & 0xffff0000u));
-            v[e] = he;
+          if ((e & 7) < POLY8) {
+            p2 = exp2_poly2(x2);
           } else {
-            if ((e & 7) < POLY8) {
-              p2 = exp2_poly2(x2);
-            } else {
-              float x0, x1, p0, p1;
-              f2_unpack(x2, x0, x1);
-              asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(x0));
-              asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(x1));
-              p2 = f2_pack(p0, p1);
-            }
-            float p0, p1;
-            f2_unpack(p2, p0, p1);
-            v[e] = pack_bf16(p0, p1);
+            float x0, x1, p0, p1;
+            f2_unpack(x2, x0, x1);
+            asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(x0));
+            asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(x1));
+            p2 = f2_pack(p0, p1);
           }
+          float p0, p1;
+          f2_unpack(p2, p0, p1);
+          v[e] = pack_bf16(p0, p1);
           if (e & 1) ls2 = f2_add(ls2, p2);
           else ls = f2_add(ls, p2);
         }
       } else {
-        u64 xq[64];                                  // x of pair e, then p of pair e (registers of v[] are recycled)
+        u64 xq[NP];                                  // x of pair e, then p of pair e (registers of v[] are recycled)
 #pragma unroll
         for (int e = 0; e < kLead; ++e)
           xq[e] = f2_fma(f2_pack(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1])), sl2_2, nmb2);
 #pragma unroll
-        for (int e = 0; e < 64 + kLag; ++e) {
-          if (e < 64) {
+        for (int e = 0; e < NP + kLag; ++e) {
+          if (e < NP) {
             float x0, x1, p0, p1;
             f2_unpack(xq[e], x0, x1);
             asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(x0));
-            if (e + kLead < 64)
+            if (e + kLead < NP)
               xq[e + kLead] = f2_fma(f2_pack(__uint_as_float(v[2 * (e + kLead)]), __uint_as_float(v[2 * (e + kLead) + 1])),
                                      sl2_2, nmb2);
             asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(x1));
@@ -353,7 +338,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
           }
         }
       }
-      if (a.pbuf && !(t == 1 && j == a.nblk - 1)) {   // hand the token to the other warpgroup
+      if (token && !(t == 1 && j == a.nblk - 1)) {   // hand the token to the other warpgroup
         if (t == 0) asm volatile("bar.arrive 3, 256;" ::: "memory");
         else asm volatile("bar.arrive 2, 256;" ::: "memory");
       }
@@ -363,9 +348,9 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
         l0 += s0;
         l1 += s1;
       }
-      // P_t -> TMEM columns [0,64) of S_t (A operand of O_t += P_t V)
-      tmem_st32(tS, v);
-      tmem_st32(tS + 32u, v + 32);
+      // P_t -> TMEM columns [0, BKV/2) of S_t (A operand of O_t += P_t V)
+#pragma unroll
+      for (int c = 0; c < NP; c += 32) tmem_st32(tS + (uint32_t)c, v + c);
       tmem_st_wait();
       tc_fence_before();
       mbar_arrive(&p_ready[t]);
@@ -411,19 +396,34 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
 int e4t_attn_make_head_map(CUtensorMap* m, const void* p, int dh, int H, int rows, int B, long long ld, long long bs,
                            int box_rows);
 
+template <int NT, int BKV, int POLY8>
+static int launch_fwd2(const CUtensorMap& mQ, const CUtensorMap& mK, const CUtensorMap& mV, const AttnArgs& a, size_t smem,
+                       cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(attn_fwd2_kernel<NT, BKV, POLY8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) !=
+        cudaSuccess)
+      return -1;
+    attr = true;
+  }
+  const dim3 grid(cdiv(a.N, 128 * NT), a.H, a.B);
+  attn_fwd2_kernel<NT, BKV, POLY8><<<grid, 128 + 128 * NT, smem, st>>>(mQ, mK, mV, a);
+  return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
 // Returns 1 if this kernel took the call, 0 if the shape is outside its envelope (caller falls back), <0 on error.
 int e4t_attn_fwd2_try(const void* Q, const void* K, const void* V, void* O, float* LSE, int B, int H, int N, int M, int dh,
                       long long ldq, long long q_bs, long long ldk, long long k_bs, long long ldv, long long v_bs,
                       long long ldo, long long o_bs, float scale, cudaStream_t st) {
   // E4T_ATTN_FWD2: "0" disables this kernel; otherwise a string of flags: 'p<k>' FMA-pipe exp2 for k of every 8 pairs,
-  // 'b' exponentials by ex2.approx.ftz.bf16x2, 'n' no exp-phase token (both warpgroups free-running)
+  // 'w' force the wide <2 tiles x 128 keys> shape, 'n' (wide shape only) no exp-phase token
   const char* e = getenv("E4T_ATTN_FWD2");
-  int poly8 = 0, f16p = 0, token = 1;
+  int poly8 = 0, wide = 0, token = 1;
   if (e) {
     if (e[0] == '0' && e[1] == 0) return 0;
     for (const char* c = e; *c; ++c) {
       if (*c == 'p' && c[1] >= '0' && c[1] <= '7') poly8 = c[1] - '0';
-      if (*c == 'b') f16p = 1;
+      if (*c == 'w') wide = 1;
       if (*c == 'n') token = 0;
     }
   }
@@ -433,13 +433,17 @@ int e4t_attn_fwd2_try(const void* Q, const void* K, const void* V, void* O, floa
   a.B = B; a.H = H; a.N = N; a.M = M; a.dh = dh;
   a.DC = cdiv(dh, 64);
   a.dpad = (dh + 15) / 16 * 16;
-  a.BKV = 128;
-  a.nblk = cdiv(M, 128);
+  // four 128-query tiles x 64-key blocks when the accumulators fit (4 x (64 + dpad) <= 512) and the query axis is
+  // long enough to fill them; otherwise two tiles x 128-key blocks
+  const bool four = !wide && a.dpad <= 64 && N >= 384;
+  const int NT = four ? 4 : 2, BKV = four ? 64 : 128;
+  a.BKV = BKV;
+  a.nblk = cdiv(M, BKV);
   a.scale = scale;
-  a.pbuf = token;     // (field reused) 1 = exp-phase token ping-pong between the two softmax warpgroups
+  a.pbuf = token;     // (field reused) 1 = exp-phase token ping-pong between the two softmax warpgroups (NT == 2)
   a.O = (bf16*)O; a.ldo = ldo; a.o_bs = o_bs; a.LSE = LSE;
-  const size_t fixed = (size_t)2 * a.DC * 16384 + 512 + 1024;
-  const size_t per_stage = (size_t)2 * a.DC * 16384;
+  const size_t fixed = (size_t)NT * a.DC * 16384 + 512 + 1024;
+  const size_t per_stage = (size_t)2 * a.DC * BKV * 128;
   int kst = (int)((227 * 1024 - fixed) / per_stage);
   if (kst > 4) kst = 4;
   if (kst > a.nblk) kst = a.nblk;
@@ -448,25 +452,19 @@ int e4t_attn_fwd2_try(const void* Q, const void* K, const void* V, void* O, floa
   const size_t smem = fixed + (size_t)kst * per_stage;
   CUtensorMap mQ, mK, mV;
   if (e4t_attn_make_head_map(&mQ, Q, dh, H, N, B, ldq, q_bs, 128)) return -1;
-  if (e4t_attn_make_head_map(&mK, K, dh, H, M, B, ldk, k_bs, 128)) return -1;
-  if (e4t_attn_make_head_map(&mV, V, dh, H, M, B, ldv, v_bs, 128)) return -1;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(attn_fwd2_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(attn_fwd2_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(attn_fwd2_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(attn_fwd2_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(attn_fwd2_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    attr = true;
+  if (e4t_attn_make_head_map(&mK, K, dh, H, M, B, ldk, k_bs, BKV)) return -1;
+  if (e4t_attn_make_head_map(&mV, V, dh, H, M, B, ldv, v_bs, BKV)) return -1;
+  if (four) {
+    switch (poly8) {
+      case 2: return launch_fwd2<4, 64, 2>(mQ, mK, mV, a, smem, st);
+      case 3: return launch_fwd2<4, 64, 3>(mQ, mK, mV, a, smem, st);
+      case 4: return launch_fwd2<4, 64, 4>(mQ, mK, mV, a, smem, st);
+      default: return launch_fwd2<4, 64, 0>(mQ, mK, mV, a, smem, st);
+    }
   }
-  const dim3 grid(cdiv(N, 256), H, B);
-  if (f16p) attn_fwd2_kernel<0, true><<<grid, 384, smem, st>>>(mQ, mK, mV, a);
-  else switch (poly8) {
-    case 2: attn_fwd2_kernel<2, false><<<grid, 384, smem, st>>>(mQ, mK, mV, a); break;
-    case 3: attn_fwd2_kernel<3, false><<<grid, 384, smem, st>>>(mQ, mK, mV, a); break;
-    case 4: attn_fwd2_kernel<4, false><<<grid, 384, smem, st>>>(mQ, mK, mV, a); break;
-    default: attn_fwd2_kernel<0, false><<<grid, 384, smem, st>>>(mQ, mK, mV, a); break;
+  switch (poly8) {
+    case 2: return launch_fwd2<2, 128, 2>(mQ, mK, mV, a, smem, st);
+    case 4: return launch_fwd2<2, 128, 4>(mQ, mK, mV, a, smem, st);
+    default: return launch_fwd2<2, 128, 0>(mQ, mK, mV, a, smem, st);
   }
-  if (cudaGetLastError() != cudaSuccess) return -1;
-  return 1;
 }

@@ -26,7 +26,8 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 static PFN_encodeTiled g_encode = nullptr;
 
 int e4t_tmap_encode(CUtensorMap* map, const void* gptr, int rank, const uint64_t* dims,
-                    const uint64_t* strides_bytes, const uint32_t* box, int elem_bytes, int swizzle_bytes) {
+                    const uint64_t* strides_bytes, const uint32_t* box, int elem_bytes, int swizzle_bytes,
+                    const uint32_t* elem_strides) {
   if (!g_encode) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -35,12 +36,20 @@ int e4t_tmap_encode(CUtensorMap* map, const void* gptr, int rank, const uint64_t
       return e4t_set_error("cuTensorMapEncodeTiled entry point unavailable (%s)", cudaGetErrorString(e));
     g_encode = (PFN_encodeTiled)fn;
   }
+  // cuTensorMapEncodeTiled is a DRIVER entry point: it needs the primary context bound to the calling thread, which the
+  // runtime only does on a thread's first runtime call.  torch's autograd worker threads can reach this function before
+  // making any (first backward of a process: CUDA_ERROR_INVALID_CONTEXT, seen in round 2) — bind it once per thread.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    cudaFree(0);
+    ctx_bound = true;
+  }
   cuuint64_t gdim[5], gstr[4];
   cuuint32_t bdim[5], estr[5];
   for (int i = 0; i < rank; ++i) {
     gdim[i] = dims[i];
     bdim[i] = box[i];
-    estr[i] = 1;
+    estr[i] = elem_strides ? elem_strides[i] : 1;
     if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
   }
   CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;

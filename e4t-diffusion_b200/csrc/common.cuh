@@ -39,7 +39,8 @@ extern unsigned long long g_e4t_launches;
 // Tensor-map encode through the driver entry point (no link-time libcuda dependency).
 int e4t_tmap_encode(CUtensorMap* map, const void* gptr, int rank, const uint64_t* dims,
                     const uint64_t* strides_bytes /* rank-1 entries, dims 1.. */,
-                    const uint32_t* box, int elem_bytes /*2 = bf16*/, int swizzle_bytes = 128);
+                    const uint32_t* box, int elem_bytes /*2 = bf16*/, int swizzle_bytes = 128,
+                    const uint32_t* elem_strides = nullptr /* traversal stride per dim (box is in global coordinates) */);
 
 static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 

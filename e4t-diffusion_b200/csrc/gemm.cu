@@ -22,6 +22,7 @@ struct GemmArgs {
   int a_mn, b_mn, a_batched, b_batched;
   // implicit 3x3 convolution (conv = 1: forward / dgrad, 2: weight gradient)
   int conv, H, W, BH, BB, cin_chunks, cout;
+  int cstride;   // spatial stride of the forward convolution (1, or 2 = Downsample2D; H, W are the OUTPUT size)
   // epilogue
   void* out;
   int out_mode;  // 0 = bf16 store, 1 = fp32 store, 2 = fp32 atomic add
@@ -90,6 +91,7 @@ e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     {
       int s = 0;
       uint32_t ph = 0;
+      bool pready = false;   // poll of empty_bar[s] issued one stage earlier (see the MMA issuer)
       for (long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int n_t = (int)(t % g.n_tiles);
         long r = t / g.n_tiles;
@@ -107,7 +109,11 @@ e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
           ch0 = (m0 % img) / g.W;
         }
         for (int kc = kc0; kc < kc1; ++kc) {
-          mbar_wait(&empty_bar[s], ph ^ 1u);
+          if (!pready) mbar_wait(&empty_bar[s], ph ^ 1u);
+          {
+            const int ns = (s + 1 == g.stages) ? 0 : s + 1;
+            pready = mbar_try_wait(&empty_bar[ns], ns == 0 ? ph : (ph ^ 1u));
+          }
           uint8_t* sA = smem + (size_t)s * stage_bytes;
           uint8_t* sB = sA + kATileBytes;
           if (g.debug & 8) {          // probe: no operand traffic at all (MMA + barrier rate on stale smem)
@@ -129,7 +135,7 @@ e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
           } else if (g.conv) {
             const int tap = kc / g.cin_chunks, cc = kc % g.cin_chunks;
             const int dy = tap / 3, dx = tap % 3;
-            tma_load_4d(sA, &mapA, &full_bar[s], cc * kBK, dx - 1, ch0 + dy - 1, cb0);
+            tma_load_4d(sA, &mapA, &full_bar[s], cc * kBK, dx - 1, g.cstride * ch0 + dy - 1, cb0);
             tma_load_2d(sB, &mapB, &full_bar[s], cc * kBK, tap * g.cout + n0);
           } else {
             const int ab = g.a_batched ? bz : 0, bb = g.b_batched ? bz : 0;
@@ -169,6 +175,10 @@ e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       const uint32_t stage_units = (uint32_t)stage_bytes >> 4;
       int s = 0, as = 0;
       uint32_t ph = 0, aph = 0;
+      // `ready`: result of a poll of full_bar[s] issued one stage EARLIER, so that the mbarrier round trip of stage s+1
+      // overlaps the descriptor arithmetic and the four tcgen05.mma issues of stage s (probe, round 2: the issue loop
+      // alone — barriers only, no TMA, no MMA — cost ~290 clk per k-chunk, more than the MMAs of a 64/128-wide tile)
+      bool ready = false;
       for (long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         long r = t / g.n_tiles / g.m_tiles;
         const int sp = (int)(r % g.splits);
@@ -178,7 +188,11 @@ e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)as * 256u;
         for (int kc = kc0; kc < kc1; ++kc) {
-          mbar_wait(&full_bar[s], ph);
+          if (!ready) mbar_wait(&full_bar[s], ph);
+          {
+            const int ns = (s + 1 == g.stages) ? 0 : s + 1;
+            ready = mbar_try_wait(&full_bar[ns], ns == 0 ? (ph ^ 1u) : ph);
+          }
           tc_fence_after();
           if (elect_one()) {
             const uint64_t da = dA0 + (uint64_t)((uint32_t)s * stage_units);
@@ -234,42 +248,51 @@ e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         // of them predicated off); this copy carries none of it.
         const bool lead_warp = (ew == 0);
         const uint32_t sw = ((uint32_t)row >> 1) & 3u;
-        uint32_t v[32];
-        int c = 32 * half;
-        if (c < g.BN && n0 + c < g.N) {
-          __syncwarp();
-          tmem_ld32(t_row + (uint32_t)c, v);
-        }
-        for (; c < g.BN && n0 + c < g.N; c += 64) {
-          tmem_ld_wait();
-          uint32_t w[16];
+        // TWO 32-column slabs of this warp are requested from TMEM at a time: a tcgen05.ld issued while the other
+        // accumulator stage is being written by MMAs takes ~600 clk (round-1 microbenchmark), and with one load in
+        // flight per warp the epilogue of a 128x256 tile (3.3 us) was longer than a K = 320 mainloop (2.1 us)
+        for (int i0 = 0; i0 < 4; i0 += 2) {
+          uint32_t v[2][32];
+          int nsl = 0;
 #pragma unroll
-          for (int q = 0; q < 16; ++q) w[q] = pack_bf16(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1]));
-          const int cn = c + 64;
-          if (cn < g.BN && n0 + cn < g.N) {
-            __syncwarp();
-            tmem_ld32(t_row + (uint32_t)cn, v);
-          }
-          uint8_t* slab = stage_c + (half + 2 * (slab_ctr & 1)) * 8192;
-          if (lead_warp) {
-            if (elect_one()) tma_store_wait_read<1>();  // the store that last read this slab has drained
-          }
-          if (half == 0) asm volatile("bar.sync 3, 128;" ::: "memory");
-          else asm volatile("bar.sync 5, 128;" ::: "memory");
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            *reinterpret_cast<uint4*>(slab + row * 64 + ((((uint32_t)q) ^ sw) << 4)) =
-                make_uint4(w[q * 4], w[q * 4 + 1], w[q * 4 + 2], w[q * 4 + 3]);
-          fence_proxy_async_smem();
-          if (half == 0) asm volatile("bar.sync 4, 128;" ::: "memory");
-          else asm volatile("bar.sync 6, 128;" ::: "memory");
-          if (lead_warp) {
-            if (elect_one()) {
-              tma_store_3d(&mapC, slab, n0 + c, m_t * kBM, bz);
-              tma_store_commit();
+          for (int i = 0; i < 2; ++i) {
+            const int c = 32 * half + 64 * (i0 + i);
+            if (c < g.BN && n0 + c < g.N) {
+              tmem_ld32(t_row + (uint32_t)c, v[i]);
+              nsl = i + 1;
             }
           }
-          ++slab_ctr;
+          if (nsl == 0) break;
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            if (i < nsl) {
+              const int c = 32 * half + 64 * (i0 + i);
+              uint32_t w[16];
+#pragma unroll
+              for (int q = 0; q < 16; ++q) w[q] = pack_bf16(__uint_as_float(v[i][2 * q]), __uint_as_float(v[i][2 * q + 1]));
+              uint8_t* slab = stage_c + (half + 2 * (slab_ctr & 1)) * 8192;
+              if (lead_warp) {
+                if (elect_one()) tma_store_wait_read<1>();  // the store that last read this slab has drained
+              }
+              if (half == 0) asm volatile("bar.sync 3, 128;" ::: "memory");
+              else asm volatile("bar.sync 5, 128;" ::: "memory");
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<uint4*>(slab + row * 64 + ((((uint32_t)q) ^ sw) << 4)) =
+                    make_uint4(w[q * 4], w[q * 4 + 1], w[q * 4 + 2], w[q * 4 + 3]);
+              fence_proxy_async_smem();
+              if (half == 0) asm volatile("bar.sync 4, 128;" ::: "memory");
+              else asm volatile("bar.sync 6, 128;" ::: "memory");
+              if (lead_warp) {
+                if (elect_one()) {
+                  tma_store_3d(&mapC, slab, n0 + c, m_t * kBM, bz);
+                  tma_store_commit();
+                }
+              }
+              ++slab_ctr;
+            }
+          }
         }
       } else if (g.tma_store) {
         // ---- bf16 output: registers -> swizzled smem slab -> TMA store (full-line coalesced writes) ----
@@ -584,30 +607,34 @@ extern "C" int e4t_gemm_bf16(const void* A, const void* B, void* out, int M, int
   return launch_gemm(mA, mB, g, stream);
 }
 
-// x: NHWC bf16 [B][H][W][Cin];  w: bf16 [9][Cout][Cin] (tap = ky*3+kx);  out: [B*H*W][Cout] (NHWC)
-// stride 1, pad 1.  bias fp32 [Cout]; rowgroup fp32 [B][Cout] (time-embedding projection) ; residual bf16 NHWC.
-extern "C" int e4t_conv3x3_bf16(const void* x, const void* w, void* out, int B, int H, int W, int Cin, int Cout,
-                                int out_mode, const float* bias, const float* rowgroup, const void* residual,
-                                int force_bn, void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
-  E4T_CHECK(Cin % 64 == 0, "e4t_conv3x3_bf16: Cin must be a multiple of 64 (got %d)", Cin);
-  E4T_CHECK(W <= 128 && (128 % W) == 0, "e4t_conv3x3_bf16: W must divide 128 (got %d)", W);
-  E4T_CHECK(out_mode == 0 || out_mode == 1, "e4t_conv3x3_bf16: bad out_mode");
+// x: NHWC bf16 [B][Hin][Win][Cin];  w: bf16 [9][Cout][Cin] (tap = ky*3+kx);  out: [B*H*W][Cout] (NHWC), H = Hin/stride.
+// pad 1.  bias fp32 [Cout]; rowgroup fp32 [B][Cout] (time-embedding projection) ; residual bf16 NHWC.
+// stride 2 (diffusers Downsample2D): the A-operand tensor map walks the input with element strides (1,2,2,1), so the
+// tile of 128 OUTPUT pixels is gathered directly from every other input pixel — no stride-1 result is computed and
+// thrown away (round 1 did exactly that: 4x the FLOPs on the three downsampling convolutions).
+static int conv3x3_impl(const void* x, const void* w, void* out, int B, int Hin, int Win, int Cin, int Cout, int stride,
+                        int out_mode, const float* bias, const float* rowgroup, const void* residual, int force_bn,
+                        cudaStream_t stream) {
+  E4T_CHECK(Cin % 64 == 0, "e4t_conv3x3: Cin must be a multiple of 64 (got %d)", Cin);
+  E4T_CHECK(stride == 1 || (stride == 2 && Hin % 2 == 0 && Win % 2 == 0), "e4t_conv3x3: bad stride/size");
+  const int H = Hin / stride, W = Win / stride;
+  E4T_CHECK(W <= 128 && (128 % W) == 0, "e4t_conv3x3: output width must divide 128 (got %d)", W);
+  E4T_CHECK(out_mode == 0 || out_mode == 1, "e4t_conv3x3: bad out_mode");
   const int img = H * W;
   int BH, BB;
   if (img >= 128) {
     BB = 1;
     BH = 128 / W;
-    E4T_CHECK(H % BH == 0, "e4t_conv3x3_bf16: H=%d not a multiple of tile height %d", H, BH);
+    E4T_CHECK(H % BH == 0, "e4t_conv3x3: H=%d not a multiple of tile height %d", H, BH);
   } else {
-    E4T_CHECK(128 % img == 0, "e4t_conv3x3_bf16: H*W must divide 128");
+    E4T_CHECK(128 % img == 0, "e4t_conv3x3: H*W must divide 128");
     BB = 128 / img;
     BH = H;
   }
   GemmArgs g;
   memset(&g, 0, sizeof(g));
   g.M = B * img; g.N = Cout; g.K = Cin; g.batch = 1;
-  g.conv = 1; g.H = H; g.W = W; g.BH = BH; g.BB = BB; g.cin_chunks = Cin / 64; g.cout = Cout;
+  g.conv = 1; g.H = H; g.W = W; g.BH = BH; g.BB = BB; g.cin_chunks = Cin / 64; g.cout = Cout; g.cstride = stride;
   g.m_tiles = cdiv(g.M, kBM);
   g.kchunks = 9 * g.cin_chunks;
   g.kper = g.kchunks; g.splits = 1;
@@ -619,10 +646,11 @@ extern "C" int e4t_conv3x3_bf16(const void* x, const void* w, void* out, int B, 
   g.alpha = 1.f;
   CUtensorMap mA, mB;
   {
-    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
-    uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)W * Cin * 2, (uint64_t)img * Cin * 2};
-    uint32_t box[4] = {kBK, (uint32_t)W, (uint32_t)BH, (uint32_t)BB};
-    if (int e = e4t_tmap_encode(&mA, x, 4, dims, str, box, 2)) return e;
+    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)Win, (uint64_t)Hin, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)Cin * 2, (uint64_t)Win * Cin * 2, (uint64_t)Hin * Win * Cin * 2};
+    uint32_t box[4] = {kBK, (uint32_t)(W * stride), (uint32_t)(BH * stride), (uint32_t)BB};
+    uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
+    if (int e = e4t_tmap_encode(&mA, x, 4, dims, str, box, 2, 128, stride == 1 ? nullptr : es)) return e;
   }
   {
     uint64_t dims[2] = {(uint64_t)Cin, (uint64_t)9 * Cout};
@@ -631,6 +659,20 @@ extern "C" int e4t_conv3x3_bf16(const void* x, const void* w, void* out, int B, 
     if (int e = e4t_tmap_encode(&mB, w, 2, dims, str, box, 2)) return e;
   }
   return launch_gemm(mA, mB, g, stream);
+}
+
+extern "C" int e4t_conv3x3_bf16(const void* x, const void* w, void* out, int B, int H, int W, int Cin, int Cout,
+                                int out_mode, const float* bias, const float* rowgroup, const void* residual,
+                                int force_bn, void* stream_) {
+  return conv3x3_impl(x, w, out, B, H, W, Cin, Cout, 1, out_mode, bias, rowgroup, residual, force_bn,
+                      (cudaStream_t)stream_);
+}
+
+// 3x3 / stride 2 / pad 1 (diffusers Downsample2D.conv, e4t/models/unet_2d_blocks.py:801-808): x [B][H][W][Cin] ->
+// out [B][H/2][W/2][Cout].
+extern "C" int e4t_conv3x3_s2_bf16(const void* x, const void* w, void* out, int B, int H, int W, int Cin, int Cout,
+                                   const float* bias, int force_bn, void* stream_) {
+  return conv3x3_impl(x, w, out, B, H, W, Cin, Cout, 2, 0, bias, nullptr, nullptr, force_bn, (cudaStream_t)stream_);
 }
 
 // 3x3 / stride 1 / pad 1 weight gradient: dw9[tap][co][ci] += sum_{b,y,x} dy[b][y][x][co] * x[b][y+ky-1][x+kx-1][ci]
@@ -648,7 +690,7 @@ extern "C" int e4t_conv3x3_wgrad(const void* x, const void* dy, float* dw9, int 
   memset(&g, 0, sizeof(g));
   g.M = Cout; g.N = Cin; g.K = (int)pixels; g.batch = 9;
   g.a_mn = 1; g.b_mn = 1; g.a_batched = 0; g.b_batched = 1;
-  g.conv = 2; g.H = H; g.W = W; g.cout = Cout;
+  g.conv = 2; g.H = H; g.W = W; g.cout = Cout; g.cstride = 1;
   g.m_tiles = cdiv(Cout, kBM);
   g.kchunks = (int)(pixels / kBK);
   // enough K-splits to fill the machine about twice: tiles = 9 taps x m_tiles x n_tiles x splits

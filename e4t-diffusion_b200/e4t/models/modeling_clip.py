@@ -86,8 +86,10 @@ class _Attention(nn.Module):
 
     def forward_kernels(self, h, residual):
         D = h.shape[-1]
-        if any(p.weight.requires_grad for p in (self.q_proj, self.k_proj, self.v_proj, self.out_proj)):
-            raise NotImplementedError("--train_text_encoder is not supported: the CLIP text tower is frozen on the E4T path")
+        if torch.is_grad_enabled() and any(p.weight.requires_grad for p in (self.q_proj, self.k_proj, self.v_proj,
+                                                                             self.out_proj)):
+            raise NotImplementedError("--train_text_encoder is not supported: freeze the CLIP text tower "
+                                      "(text_encoder.requires_grad_(False), pretrain_e4t.py:262-263)")
         w, b = self._qkv()
         qkv = FN.LinearFn.apply(h, w, b, None, None)
         o = FN.SmallAttentionFn.apply(qkv, self.heads, (D // self.heads) ** -0.5, True)   # causal (modeling_clip.py:45-47)

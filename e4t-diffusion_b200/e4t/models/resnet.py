@@ -63,9 +63,9 @@ class Downsample2D(nn.Module):
             self.conv = conv
 
     def forward(self, hidden_states):
-        # stride-2 conv == stride-1 conv sampled at even positions (round-1 formulation; 4x the minimal FLOPs on
-        # three small layers, 5.7 GF/img — SURVEY.md §8 a-9)
-        return FN.ResampleFn.apply(conv3x3(self.conv, hidden_states), 2)
+        # stride-2 convolution computed directly at the output resolution
+        c = self.conv
+        return FN.Conv3x3S2Fn.apply(hidden_states, conv_w9(c), conv_w9_dgrad(c), c.bias, c.weight)
 
 
 class ResnetBlock2D(nn.Module):

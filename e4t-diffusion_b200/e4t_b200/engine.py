@@ -7,6 +7,8 @@ reference gets from accelerate/torch.optim rebuilt B200-first:
                     (reference: DDP buckets over every requires_grad parameter, ≈4.9 GB; here 1.5 GB).
   * PretrainStep  — the loop body given explicit (pixel_values, latents, noise, timesteps, input_ids).
 """
+import os
+
 import torch
 import torch.distributed as dist
 import torch.nn.functional as F
@@ -89,6 +91,10 @@ class FlatAdamW:
                     p.data = self.arena[o:o + p.numel()].view(p.shape)
                     p.grad = self.grad[o:o + p.numel()].view(p.shape)
                     p._e4t_arena = True
+        self.offsets = {}                                                # id(param) -> (offset, numel) in the arena
+        for ps, base, n, off in layout:
+            for p in ps:
+                self.offsets[id(p)] = (off + (p.data_ptr() - self.arena.data_ptr()) // 4 - off, p.numel())
         self.step_count = 0
         self.step_dev = torch.zeros(1, device=dev, dtype=torch.int32)   # device-side counter: graph-replayable
         FN.DIRECT_GRAD_WRITE = True     # .grad views are zeroed by zero_grad(); WO kernels write them directly
@@ -98,10 +104,21 @@ class FlatAdamW:
     def zero_grad(self, set_to_none=False):
         self.grad.zero_()
 
-    def all_reduce_grads(self):
-        """Data-parallel gradient exchange: one NCCL all-reduce (SUM) of the gradient arena; the 1/world average
-        is folded into the optimiser kernel's grad_scale."""
-        return all_reduce_sum_(self.grad, self.process_group)
+    def all_reduce_grads(self, start=0, end=None):
+        """Data-parallel gradient exchange: NCCL all-reduce (SUM) of the gradient arena (or of the slice
+        [start, end)); the 1/world average is folded into the optimiser kernel's grad_scale."""
+        g = self.grad if (start == 0 and end is None) else self.grad[start:end]
+        return all_reduce_sum_(g, self.process_group)
+
+    def prefix_end(self, params):
+        """End offset of the arena prefix that holds exactly `params` (None if they are not a contiguous prefix)."""
+        ids = {id(p) for p in params}
+        if not ids:
+            return None
+        end = max(self.offsets[i][0] + self.offsets[i][1] for i in ids)
+        inside = sum(n for i, (o, n) in self.offsets.items() if o < end)
+        mine = sum(self.offsets[i][1] for i in ids)
+        return (end + 3) // 4 * 4 if inside == mine else None
 
     def step(self, grad_scale=1.0):
         self.step_count += 1
@@ -169,6 +186,19 @@ class PretrainStep:
                              weight_decay=weight_decay, eps=eps) if optimizer else None
         self._graph = None
         self.wo_bank = None
+        # Data parallel: the encoder-head gradients (925 MB of the 1.5 GB arena, an arena prefix) are final as soon as
+        # the head's backward has run — before the encoder-half UNet backward.  Their all-reduce is issued at that
+        # moment on a communication stream and overlaps that backward; only the WeightOffsets slice (produced by the
+        # bank at the very end of backward) is exchanged after it.  (Round 1: one exposed 1.5 GB all-reduce, 3.8 ms.)
+        self._comm = None
+        self._early_end = None
+        self._early_fired = False
+        if (self.opt is not None and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+                and not any(p.requires_grad for p in e4t_encoder.clip_vision.parameters())):
+            self._early_end = self.opt.prefix_end([p for p in e4t_encoder.parameters() if p.requires_grad])
+            if self._early_end is not None:
+                self._comm = torch.cuda.Stream()
+                FN.GRAD_READY_HOOKS["encoder_head"] = self._early_all_reduce
         if self.opt is not None:
             from .wobank import WOBank
             from e4t.models.cross_attention import CrossAttention
@@ -224,8 +254,7 @@ class PretrainStep:
         # Data parallel runs keep the NCCL all-reduce and the optimiser kernel OUTSIDE the graph (three eager launches):
         # collectives captured into a graph must be captured identically on every rank and interact with the
         # process-group watchdog; the compute part (forward + backward) is what has thousands of launches.
-        self._graph_has_opt = not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1)
-        body = self._eager_step if self._graph_has_opt else self._fwd_bwd
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
         with torch.cuda.stream(side):
             for _ in range(warmup):
                 out = self._eager_step(self._static)
@@ -234,12 +263,37 @@ class PretrainStep:
         gc.collect()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        mode = "global" if self._graph_has_opt else "thread_local"   # NCCL's watchdog thread polls events
-        with torch.cuda.graph(graph, stream=side, capture_error_mode=mode):
-            out = body(self._static)
-            self._static_out = {k: out[k].detach() for k in ("loss", "loss_diff", "loss_reg")}
-            del out
+
+        def capture(body, mode):
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side, capture_error_mode=mode):
+                out = body(self._static)
+                self._static_out = {k: out[k].detach() for k in ("loss", "loss_diff", "loss_reg")}
+                del out
+            return graph
+
+        # Data parallel: first try to capture the WHOLE step including the NCCL all-reduces (forked onto the comm stream
+        # inside the capture) and AdamW; if this torch/NCCL build refuses, capture forward+backward only and keep the
+        # exchange + optimiser as three eager launches (the round-1 behaviour).
+        self._graph_has_opt = True
+        if multi and os.environ.get("E4T_GRAPH_NCCL", "1") != "0":
+            try:
+                graph = capture(self._eager_step, "thread_local")
+            except Exception as ex:   # noqa: BLE001
+                self._capture_note = f"NCCL-in-graph capture failed ({type(ex).__name__}: {str(ex)[:120]}); compute-only graph"
+                self._early_fired = False
+                self._comm = None               # no collective inside the compute-only graph
+                torch.cuda.synchronize()
+                self._drop_autograd_refs()
+                gc.collect()
+                self._graph_has_opt = False
+                graph = capture(self._fwd_bwd, "thread_local")
+        elif multi:
+            self._comm = None
+            self._graph_has_opt = False
+            graph = capture(self._fwd_bwd, "thread_local")
+        else:
+            graph = capture(self._eager_step, "global")
         self._drop_autograd_refs()
         self._graph = graph
         return self
@@ -268,9 +322,24 @@ class PretrainStep:
         out["loss"].backward()                                                           # :648
         return out
 
+    def _early_all_reduce(self):
+        """Fired from inside backward (functional.MeanPoolCatFn): all-reduce the encoder-head slice on the comm stream."""
+        if self._comm is None or self._early_fired:
+            return
+        main = torch.cuda.current_stream()
+        self._comm.wait_stream(main)
+        with torch.cuda.stream(self._comm):
+            self.opt.all_reduce_grads(0, self._early_end)
+        self._early_fired = True
+
     def _apply_optimizer(self):
         if self.opt is not None:
-            scale = self.opt.all_reduce_grads()
+            if self._early_fired:
+                torch.cuda.current_stream().wait_stream(self._comm)
+                scale = self.opt.all_reduce_grads(self._early_end, None)
+                self._early_fired = False
+            else:
+                scale = self.opt.all_reduce_grads()
             if self.max_grad_norm is not None:
                 # accelerator.clip_grad_norm_ (tuning_e4t.py:329-335) == torch clip_grad_norm_: one norm over the flat
                 # gradient arena (its padding is zero), coefficient kept on the device (graph-replayable)

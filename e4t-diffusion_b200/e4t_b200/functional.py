@@ -24,6 +24,15 @@ def bump_param_epoch():
     PARAM_EPOCH += 1
 
 
+GRAD_READY_HOOKS = {}  # name -> callable, fired from inside backward when a group of gradients is final (engine.py)
+
+
+def fire_grad_ready(name):
+    h = GRAD_READY_HOOKS.get(name)
+    if h is not None:
+        h()
+
+
 NOGRAD_FWD_EPOCH = 0  # bumped by every no-grad UNet forward: W_eff is then always rebuilt from the current parameters
 
 
@@ -80,7 +89,7 @@ class LinearFn(torch.autograd.Function):
         x2 = _c(x).view(-1, shp[-1])
         res2 = None if residual is None else _c(residual).view(-1, w.shape[0])
         y = ops.gemm(x2, w, bias=bias, residual=res2)
-        need_dw = wp is not None and wp.requires_grad and torch.is_grad_enabled()
+        need_dw = wp is not None and ctx.needs_input_grad[4]     # (grad mode is off inside forward: ask ctx)
         ctx.save_for_backward(w, x2 if need_dw else None)
         ctx.shp = shp
         ctx.has_res = residual is not None
@@ -198,7 +207,7 @@ class Conv3x3Fn(torch.autograd.Function):
     def forward(ctx, x, w9, w9_dgrad, bias, rowgroup, residual, wp=None):
         x = _c(x)
         y = ops.conv3x3(x, w9, bias=bias, rowgroup=rowgroup, residual=None if residual is None else _c(residual))
-        need_dw = wp is not None and wp.requires_grad and torch.is_grad_enabled()
+        need_dw = wp is not None and ctx.needs_input_grad[6]
         ctx.save_for_backward(w9_dgrad, x if need_dw else None)
         ctx.has_res = residual is not None
         return y
@@ -221,6 +230,35 @@ class Conv3x3Fn(torch.autograd.Function):
         return dx, None, None, db, drow, (dy if ctx.has_res else None), dw
 
 
+class Conv3x3S2Fn(torch.autograd.Function):
+    """3x3 / stride 2 / pad 1 convolution (diffusers Downsample2D) computed directly at the output resolution (the
+    implicit-GEMM A operand is gathered with TMA element strides).  Backward: dY is zero-inserted to the input
+    resolution (the adjoint of the stride-2 pick) and then follows the stride-1 paths: dX by the dgrad convolution,
+    dW / db (only when trainable) by the weight-gradient kernels."""
+
+    @staticmethod
+    def forward(ctx, x, w9, w9_dgrad, bias, wp=None):
+        x = _c(x)
+        y = ops.conv3x3_s2(x, w9, bias=bias)
+        need_dw = wp is not None and ctx.needs_input_grad[4]
+        ctx.save_for_backward(w9_dgrad, x if need_dw else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        w9_dgrad, x = ctx.saved_tensors
+        dy = _c(dy)
+        Cout = dy.shape[-1]
+        up = ops.resample2x(dy, 3)                                              # zero insertion
+        dx = ops.conv3x3(up, w9_dgrad) if ctx.needs_input_grad[0] else None
+        db = dw = None
+        if ctx.needs_input_grad[3]:
+            db = ops.colsum_acc(dy.view(-1, Cout), torch.zeros(Cout, device=dy.device, dtype=F32))
+        if len(ctx.needs_input_grad) > 4 and ctx.needs_input_grad[4] and x is not None:
+            dw = ops.conv3x3_wgrad(x, up).view(3, 3, Cout, -1).permute(2, 3, 0, 1).contiguous()
+        return dx, None, None, db, dw
+
+
 class ResampleFn(torch.autograd.Function):
     """mode 0: nearest x2 upsample; mode 2: stride-2 pick.  Backward is the adjoint kernel (modes 1 / 3)."""
 
@@ -240,7 +278,7 @@ class ConvOutFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, bias):
         x = _c(x)
-        need_dw = w.requires_grad and torch.is_grad_enabled()
+        need_dw = ctx.needs_input_grad[1]
         ctx.save_for_backward(w, x if need_dw else None)
         ctx.C = x.shape[-1]
         return ops.conv_out_fwd(x, w.detach(), bias.detach())
@@ -266,7 +304,7 @@ class ConvInFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, sample, w, bias):
         sample = _c(sample.detach().float())
-        need_dw = w.requires_grad and torch.is_grad_enabled()
+        need_dw = ctx.needs_input_grad[1]
         ctx.save_for_backward(sample if need_dw else None)
         ctx.wshape = tuple(w.shape)
         return ops.conv_in_fwd(sample, w.detach(), bias.detach())
@@ -522,6 +560,9 @@ class MeanPoolCatFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout):
+        # every E4TEncoder-head gradient is final here (this is the head's first forward op, so its last backward op):
+        # the data-parallel engine starts their all-reduce now, under the encoder-half UNet backward that follows
+        fire_grad_ready("encoder_head")
         dout = _c(dout.float())
         outs = []
         off = 0

@@ -86,6 +86,17 @@ def conv3x3(x, w9, *, bias=None, rowgroup=None, residual=None, out_dtype=BF16, f
     return out
 
 
+def conv3x3_s2(x, w9, *, bias=None, force_bn=0):
+    """3x3 stride-2 pad-1 convolution on NHWC bf16 (Downsample2D): (B,H,W,Cin) -> (B,H/2,W/2,Cout)."""
+    assert x.dtype == BF16 and w9.dtype == BF16 and x.is_contiguous() and w9.is_contiguous()
+    Bn, H, W, Cin = x.shape
+    Cout = w9.shape[1]
+    out = torch.empty((Bn, H // 2, W // 2, Cout), device=x.device, dtype=BF16)
+    _lib.call("e4t_conv3x3_s2_bf16", ptr(x), ptr(w9), ptr(out), c_int(Bn), c_int(H), c_int(W), c_int(Cin), c_int(Cout),
+              ptr(bias), c_int(force_bn), stream())
+    return out
+
+
 # ----------------------------------------------------------------------------------------------
 # normalisation
 # ----------------------------------------------------------------------------------------------

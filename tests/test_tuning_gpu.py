@@ -210,3 +210,26 @@ def test_tuning_step_tiny_vs_oracle_adamw_with_clipping():
     print("[tuning step] oracle", [round(v, 5) for v in lo], "cuda", [round(v, 5) for v in lg])
     for a, b in zip(lo, lg):
         assert abs(a - b) <= 3e-2 * abs(a) + 1e-4, (lo, lg)
+
+
+@pytest.mark.parametrize("B,H,Cin,Cout", [(2, 64, 64, 64), (2, 32, 128, 192), (4, 16, 320, 320)])
+def test_conv3x3_stride2_fwd_bwd(B, H, Cin, Cout):
+    """Downsample2D: stride-2 convolution computed at the output resolution (TMA element strides) vs F.conv2d."""
+    from e4t_b200 import functional as FN
+    g = torch.Generator(device="cuda").manual_seed(H + Cout)
+    x = _mk((B, H, H, Cin), g).requires_grad_(True)
+    conv = torch.nn.Conv2d(Cin, Cout, 3, stride=2, padding=1).cuda()
+    with torch.no_grad():
+        conv.weight.copy_(conv.weight.to(torch.bfloat16).float())
+    w9 = conv.weight.detach().permute(2, 3, 0, 1).reshape(9, Cout, Cin).to(torch.bfloat16).contiguous()
+    w9d = conv.weight.detach().flip(2, 3).permute(2, 3, 1, 0).reshape(9, Cin, Cout).to(torch.bfloat16).contiguous()
+    dy = _mk((B, H // 2, H // 2, Cout), g)
+    y = FN.Conv3x3S2Fn.apply(x, w9, w9d, conv.bias, conv.weight)
+    y.backward(dy)
+    xr = x.detach().float().permute(0, 3, 1, 2).requires_grad_(True)
+    wr, br = conv.weight.detach().clone().requires_grad_(True), conv.bias.detach().clone().requires_grad_(True)
+    yr = F.conv2d(xr, wr, br, stride=2, padding=1)
+    yr.backward(dy.float().permute(0, 3, 1, 2))
+    assert _rel(y.permute(0, 3, 1, 2), yr) < 6e-3, _rel(y.permute(0, 3, 1, 2), yr)
+    assert _rel(x.grad.permute(0, 3, 1, 2), xr.grad) < 6e-3
+    assert _rel(conv.weight.grad, wr.grad) < 3e-3 and _rel(conv.bias.grad, br.grad) < 2e-3
