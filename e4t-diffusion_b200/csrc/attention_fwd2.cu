@@ -416,14 +416,14 @@ int e4t_attn_fwd2_try(const void* Q, const void* K, const void* V, void* O, floa
                       long long ldq, long long q_bs, long long ldk, long long k_bs, long long ldv, long long v_bs,
                       long long ldo, long long o_bs, float scale, cudaStream_t st) {
   // E4T_ATTN_FWD2: "0" disables this kernel; otherwise a string of flags: 'p<k>' FMA-pipe exp2 for k of every 8 pairs,
-  // 'w' force the wide <2 tiles x 128 keys> shape, 'n' (wide shape only) no exp-phase token
+  // 'f' select the <4 tiles x 64 keys> shape (measured slower, see below), 'n' no exp-phase token
   const char* e = getenv("E4T_ATTN_FWD2");
-  int poly8 = 0, wide = 0, token = 1;
+  int poly8 = 0, wide = 1, token = 1;
   if (e) {
     if (e[0] == '0' && e[1] == 0) return 0;
     for (const char* c = e; *c; ++c) {
       if (*c == 'p' && c[1] >= '0' && c[1] <= '7') poly8 = c[1] - '0';
-      if (*c == 'w') wide = 1;
+      if (*c == 'f') wide = 0;
       if (*c == 'n') token = 0;
     }
   }
@@ -433,8 +433,11 @@ int e4t_attn_fwd2_try(const void* Q, const void* K, const void* V, void* O, floa
   a.B = B; a.H = H; a.N = N; a.M = M; a.dh = dh;
   a.DC = cdiv(dh, 64);
   a.dpad = (dh + 15) / 16 * 16;
-  // four 128-query tiles x 64-key blocks when the accumulators fit (4 x (64 + dpad) <= 512) and the query axis is
-  // long enough to fill them; otherwise two tiles x 128-key blocks
+  // default: two 128-query tiles x 128-key blocks.  The four-tile x 64-key shape (flag 'f'; accumulators fit when
+  // 4 x (64 + dpad) <= 512) was built to put four row-private softmax warps on every sub-partition, but measured
+  // SLOWER at the level-0 shape (0.947 ms vs 0.906 ms, r02 call 6): with 64-key blocks the per-tile dependency loop
+  // softmax -> P ready -> P·V, Q·K^T issue -> S ready is paid twice as often and its latency (mbarrier wake-ups, ~600 clk
+  // tcgen05.ld under MMA load), not MUFU throughput, then dominates — the softmax warps wait 67 % of the time for S.
   const bool four = !wide && a.dpad <= 64 && N >= 384;
   const int NT = four ? 4 : 2, BKV = four ? 64 : 128;
   a.BKV = BKV;

@@ -35,6 +35,7 @@ struct GemmArgs {
   float alpha;
   int debug;      // E4T_GEMM_DEBUG probes: 1 skip epilogue body, 4 skip output staging, 8 no TMA loads, 16 no MMAs
   int tma_store;  // bf16 output through smem staging + TMA store (coalesced, asynchronous)
+  int poll_ahead; // opt-in: poll the next stage's mbarrier one stage ahead (test_wait)
   int epi_plain;  // default on (E4T_GEMM_EPI_PLAIN=0 disables): separate slab loop for outputs without alpha/bias/rowgroup/residual
 };
 
@@ -110,9 +111,10 @@ e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         }
         for (int kc = kc0; kc < kc1; ++kc) {
           if (!pready) mbar_wait(&empty_bar[s], ph ^ 1u);
-          {
+          pready = false;
+          if (g.poll_ahead) {
             const int ns = (s + 1 == g.stages) ? 0 : s + 1;
-            pready = mbar_try_wait(&empty_bar[ns], ns == 0 ? ph : (ph ^ 1u));
+            pready = mbar_test_wait(&empty_bar[ns], ns == 0 ? ph : (ph ^ 1u));
           }
           uint8_t* sA = smem + (size_t)s * stage_bytes;
           uint8_t* sB = sA + kATileBytes;
@@ -175,9 +177,10 @@ e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       const uint32_t stage_units = (uint32_t)stage_bytes >> 4;
       int s = 0, as = 0;
       uint32_t ph = 0, aph = 0;
-      // `ready`: result of a poll of full_bar[s] issued one stage EARLIER, so that the mbarrier round trip of stage s+1
-      // overlaps the descriptor arithmetic and the four tcgen05.mma issues of stage s (probe, round 2: the issue loop
-      // alone — barriers only, no TMA, no MMA — cost ~290 clk per k-chunk, more than the MMAs of a 64/128-wide tile)
+      // `ready` (opt-in, E4T_GEMM_POLL=1): result of a NON-blocking poll (mbarrier.test_wait) of full_bar[s] issued one
+      // stage earlier, so that the mbarrier round trip of stage s+1 overlaps the tcgen05.mma issues of stage s (probe,
+      // round 2: the issue loop alone — barriers only — costs ~290 clk per k-chunk).  A try_wait here was measured to be
+      // 1.5x SLOWER: it may suspend the thread for a system-defined time when the phase is incomplete.
       bool ready = false;
       for (long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         long r = t / g.n_tiles / g.m_tiles;
@@ -189,9 +192,10 @@ e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         const uint32_t d_tmem = tmem_base + (uint32_t)as * 256u;
         for (int kc = kc0; kc < kc1; ++kc) {
           if (!ready) mbar_wait(&full_bar[s], ph);
-          {
+          ready = false;
+          if (g.poll_ahead) {
             const int ns = (s + 1 == g.stages) ? 0 : s + 1;
-            ready = mbar_try_wait(&full_bar[ns], ns == 0 ? (ph ^ 1u) : ph);
+            ready = mbar_test_wait(&full_bar[ns], ns == 0 ? (ph ^ 1u) : ph);
           }
           tc_fence_after();
           if (elect_one()) {
@@ -248,51 +252,42 @@ e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         // of them predicated off); this copy carries none of it.
         const bool lead_warp = (ew == 0);
         const uint32_t sw = ((uint32_t)row >> 1) & 3u;
-        // TWO 32-column slabs of this warp are requested from TMEM at a time: a tcgen05.ld issued while the other
-        // accumulator stage is being written by MMAs takes ~600 clk (round-1 microbenchmark), and with one load in
-        // flight per warp the epilogue of a 128x256 tile (3.3 us) was longer than a K = 320 mainloop (2.1 us)
-        for (int i0 = 0; i0 < 4; i0 += 2) {
-          uint32_t v[2][32];
-          int nsl = 0;
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const int c = 32 * half + 64 * (i0 + i);
-            if (c < g.BN && n0 + c < g.N) {
-              tmem_ld32(t_row + (uint32_t)c, v[i]);
-              nsl = i + 1;
-            }
-          }
-          if (nsl == 0) break;
+        uint32_t v[32];
+        int c = 32 * half;
+        if (c < g.BN && n0 + c < g.N) {
+          __syncwarp();
+          tmem_ld32(t_row + (uint32_t)c, v);
+        }
+        for (; c < g.BN && n0 + c < g.N; c += 64) {
           tmem_ld_wait();
+          uint32_t w[16];
 #pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            if (i < nsl) {
-              const int c = 32 * half + 64 * (i0 + i);
-              uint32_t w[16];
+          for (int q = 0; q < 16; ++q) w[q] = pack_bf16(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1]));
+          const int cn = c + 64;
+          if (cn < g.BN && n0 + cn < g.N) {
+            __syncwarp();
+            tmem_ld32(t_row + (uint32_t)cn, v);
+          }
+          uint8_t* slab = stage_c + (half + 2 * (slab_ctr & 1)) * 8192;
+          if (lead_warp) {
+            if (elect_one()) tma_store_wait_read<1>();  // the store that last read this slab has drained
+          }
+          if (half == 0) asm volatile("bar.sync 3, 128;" ::: "memory");
+          else asm volatile("bar.sync 5, 128;" ::: "memory");
 #pragma unroll
-              for (int q = 0; q < 16; ++q) w[q] = pack_bf16(__uint_as_float(v[i][2 * q]), __uint_as_float(v[i][2 * q + 1]));
-              uint8_t* slab = stage_c + (half + 2 * (slab_ctr & 1)) * 8192;
-              if (lead_warp) {
-                if (elect_one()) tma_store_wait_read<1>();  // the store that last read this slab has drained
-              }
-              if (half == 0) asm volatile("bar.sync 3, 128;" ::: "memory");
-              else asm volatile("bar.sync 5, 128;" ::: "memory");
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-                *reinterpret_cast<uint4*>(slab + row * 64 + ((((uint32_t)q) ^ sw) << 4)) =
-                    make_uint4(w[q * 4], w[q * 4 + 1], w[q * 4 + 2], w[q * 4 + 3]);
-              fence_proxy_async_smem();
-              if (half == 0) asm volatile("bar.sync 4, 128;" ::: "memory");
-              else asm volatile("bar.sync 6, 128;" ::: "memory");
-              if (lead_warp) {
-                if (elect_one()) {
-                  tma_store_3d(&mapC, slab, n0 + c, m_t * kBM, bz);
-                  tma_store_commit();
-                }
-              }
-              ++slab_ctr;
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<uint4*>(slab + row * 64 + ((((uint32_t)q) ^ sw) << 4)) =
+                make_uint4(w[q * 4], w[q * 4 + 1], w[q * 4 + 2], w[q * 4 + 3]);
+          fence_proxy_async_smem();
+          if (half == 0) asm volatile("bar.sync 4, 128;" ::: "memory");
+          else asm volatile("bar.sync 6, 128;" ::: "memory");
+          if (lead_warp) {
+            if (elect_one()) {
+              tma_store_3d(&mapC, slab, n0 + c, m_t * kBM, bz);
+              tma_store_commit();
             }
           }
+          ++slab_ctr;
         }
       } else if (g.tma_store) {
         // ---- bf16 output: registers -> swizzled smem slab -> TMA store (full-line coalesced writes) ----
@@ -507,6 +502,8 @@ static int launch_gemm(const CUtensorMap& mA, const CUtensorMap& mB, GemmArgs& g
   {
     const char* d = getenv("E4T_GEMM_DEBUG");
     g.debug = d ? atoi(d) : 0;
+    const char* pa = getenv("E4T_GEMM_POLL");
+    g.poll_ahead = pa ? atoi(pa) : 0;
     const char* p = getenv("E4T_GEMM_EPI_PLAIN");   // default ON (bit-identical on all 40 step signatures, r02 sweep)
     g.epi_plain = p ? atoi(p) : 1;
   }

@@ -20,8 +20,16 @@ struct GNChan {
   float mean, rstd, gamma, beta;
 };
 
+// sigmoid through ONE MUFU operation (tanh.approx, |err| ~ 2^-11): the exp + reciprocal form costs two, and the
+// GroupNorm+SiLU apply pass was 47 % MUFU-busy (ncu r02) on top of its memory traffic
+__device__ __forceinline__ float sigmoid_fast(float y) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * y));
+  return fmaf(0.5f, t, 0.5f);
+}
+__device__ __forceinline__ float silu_fast(float y) { return y * sigmoid_fast(y); }
 __device__ __forceinline__ float silu_grad(float y) {
-  const float sg = 1.f / (1.f + __expf(-y));
+  const float sg = sigmoid_fast(y);
   return sg * (1.f + y * (1.f - sg));
 }
 __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
@@ -146,7 +154,7 @@ gn_apply_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, const f
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         o[j] = fmaf(xv[j], scale[j], shift[j]);
-        if (act) o[j] = silu_f(o[j]);
+        if (act) o[j] = silu_fast(o[j]);
       }
     } else {
       float dv[8];
@@ -168,12 +176,26 @@ static int gn_env(const char* name) {
   const char* e = getenv(name);
   return e ? atoi(e) : 0;
 }
-static int gn_rows_per_cta(int B, int HW) {
+// rows per CTA such that the grid is (about) ONE full wave of resident CTAs: the round-1 choice (64 rows, >= 8 CTAs per
+// SM "overall") gave 1.73 waves at the 16 x 1024 x 1280 shape, i.e. a second wave that is three-quarters empty
+template <typename K>
+static int gn_rows_per_cta(K kernel, int threads, size_t smem_per_rl, int C, int B, int HW) {
   const int forced = gn_env("E4T_GN_ROWS");
   if (forced > 0) return forced;
-  // aim for >= ~8 CTAs per SM overall
-  int rows = 64;
-  while (rows > 4 && (long)B * cdiv(HW, rows) < 148 * 8) rows >>= 1;
+  int occ = 0;
+  const size_t smem = smem_per_rl * (size_t)(threads / (C / 8));
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem) != cudaSuccess || occ < 1) occ = 4;
+  int sms = 0, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (sms <= 0) sms = 148;
+  const long target = (long)sms * occ;
+  long chunks = target / B;                 // row chunks per image
+  if (chunks < 1) chunks = 1;
+  if (chunks > HW) chunks = HW;
+  int rows = cdiv(HW, chunks);
+  const int rstep = threads / (C / 8);
+  if (rows < rstep) rows = rstep;           // at least one row per concurrent row lane
   return rows;
 }
 static int gn_block(int C) {
@@ -191,15 +213,16 @@ extern "C" int e4t_groupnorm_fwd(const void* x, const float* gamma, const float*
   cudaStream_t st = (cudaStream_t)stream_;
   E4T_CHECK(C % G == 0 && C % 8 == 0 && C / 8 <= kGNMaxThreads, "e4t_groupnorm_fwd: unsupported C=%d G=%d", C, G);
   E4T_CUDA(cudaMemsetAsync(stats, 0, (size_t)B * G * 2 * sizeof(float), st));
-  const int rows = gn_rows_per_cta(B, HW);
   const int threads = gn_block(C);
+  const int rows = gn_rows_per_cta(gn_stats_kernel<0>, threads, (size_t)C * sizeof(float2), C, B, HW);
   dim3 grid(cdiv(HW, rows), B);
   gn_stats_kernel<0><<<grid, threads, (size_t)(threads / (C / 8)) * C * sizeof(float2), st>>>((const bf16*)x, nullptr, nullptr, nullptr,
                                                                         nullptr, stats, HW, C, G, rows, eps, 0);
   E4T_COUNT_LAUNCH();
   E4T_LAUNCH_CHECK();
-  gn_apply_kernel<0><<<grid, threads, 0, st>>>((const bf16*)x, nullptr, stats, nullptr, gamma, beta, (bf16*)y, HW, C, G,
-                                               rows, eps, act_silu);
+  const int rows_a = gn_rows_per_cta(gn_apply_kernel<0>, threads, 0, C, B, HW);
+  gn_apply_kernel<0><<<dim3(cdiv(HW, rows_a), B), threads, 0, st>>>((const bf16*)x, nullptr, stats, nullptr, gamma, beta,
+                                                                    (bf16*)y, HW, C, G, rows_a, eps, act_silu);
   E4T_COUNT_LAUNCH();
   E4T_LAUNCH_CHECK();
   return 0;
@@ -212,15 +235,16 @@ extern "C" int e4t_groupnorm_bwd(const void* x, const void* dy, const float* gam
   cudaStream_t st = (cudaStream_t)stream_;
   E4T_CHECK(C % G == 0 && C % 8 == 0 && C / 8 <= kGNMaxThreads, "e4t_groupnorm_bwd: unsupported C=%d G=%d", C, G);
   E4T_CUDA(cudaMemsetAsync(scratch, 0, (size_t)B * G * 2 * sizeof(float), st));
-  const int rows = gn_rows_per_cta(B, HW);
   const int threads = gn_block(C);
+  const int rows = gn_rows_per_cta(gn_stats_kernel<1>, threads, (size_t)C * sizeof(float2), C, B, HW);
   dim3 grid(cdiv(HW, rows), B);
   gn_stats_kernel<1><<<grid, threads, (size_t)(threads / (C / 8)) * C * sizeof(float2), st>>>((const bf16*)x, (const bf16*)dy, stats, gamma,
                                                                         beta, scratch, HW, C, G, rows, eps, act_silu);
   E4T_COUNT_LAUNCH();
   E4T_LAUNCH_CHECK();
-  gn_apply_kernel<1><<<grid, threads, 0, st>>>((const bf16*)x, (const bf16*)dy, stats, scratch, gamma, beta, (bf16*)dx,
-                                               HW, C, G, rows, eps, act_silu);
+  const int rows_a = gn_rows_per_cta(gn_apply_kernel<1>, threads, 0, C, B, HW);
+  gn_apply_kernel<1><<<dim3(cdiv(HW, rows_a), B), threads, 0, st>>>((const bf16*)x, (const bf16*)dy, stats, scratch, gamma,
+                                                                    beta, (bf16*)dx, HW, C, G, rows_a, eps, act_silu);
   E4T_COUNT_LAUNCH();
   E4T_LAUNCH_CHECK();
   return 0;
