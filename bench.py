@@ -43,6 +43,12 @@ def parse():
     ap.add_argument("--no-micro", action="store_true")
     ap.add_argument("--profile-one-step", action="store_true", help="run W warm-up + 1 step and exit (for ncu)")
     ap.add_argument("--no-graph", action="store_true", help="eager launches instead of the whole-step CUDA graph")
+    ap.add_argument("--unfreeze-clip-vision", action="store_true",
+                    help="the README recipe's variant (README.md:52, pretrain_e4t.py:78,249): the ViT-H/14 tower trains too "
+                         "(+630.8 M parameters in the optimiser and the all-reduce); reported separately, SURVEY.md §8d")
+    ap.add_argument("--tuning", action="store_true",
+                    help="BASELINE configs[3]: the domain-tuning step (tuning_e4t.py:270-338): every UNet weight trainable, "
+                         "one image repeated over the batch, grad-norm clipping at 1.0")
     return ap.parse_args()
 
 
@@ -112,14 +118,14 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------------------
 # model / data
 # ------------------------------------------------------------------------------------------------------------------
-def build_models(device):
+def build_models(device, freeze_clip_vision=True):
     from e4t.encoder import E4TEncoder
     from e4t.models.modeling_clip import CLIPTextConfig, CLIPTextModel
     from e4t.models.unet_2d_condition import UNet2DConditionModel
     torch.manual_seed(0)
     with torch.device(device):
         unet = UNet2DConditionModel(cross_attention_dim=768, sample_size=64)     # SD-v1.4 config (defaults + 768)
-        enc = E4TEncoder(word_embedding_dim=768, arch="ViT-H-14")
+        enc = E4TEncoder(word_embedding_dim=768, arch="ViT-H-14", freeze_clip_vision=freeze_clip_vision)
         text = CLIPTextModel(CLIPTextConfig(vocab_size=49409))
     text.to(torch.bfloat16)                                                      # pretrain_e4t.py:422-423
     return unet, enc, text
@@ -434,9 +440,14 @@ def main():
     peaks = load_peaks()
     B = args.batch
 
-    unet, enc, text = build_models(device)
-    step = PretrainStep(unet, enc, text, placeholder_token_id=49408, class_token_id=320, lr=1.6e-5,
-                        weight_dtype=torch.bfloat16)
+    unet, enc, text = build_models(device, freeze_clip_vision=not args.unfreeze_clip_vision)
+    if args.tuning:
+        from e4t_b200.engine import TuningStep
+        step = TuningStep(unet, enc, text, placeholder_token_id=49408, class_token_id=320, lr=1.6e-5,
+                          weight_dtype=torch.bfloat16)
+    else:
+        step = PretrainStep(unet, enc, text, placeholder_token_id=49408, class_token_id=320, lr=1.6e-5,
+                            weight_dtype=torch.bfloat16)
     n_train = step.opt.numel
 
     def barrier():
@@ -469,6 +480,10 @@ def main():
         return t, (last if isinstance(last, float) else float(last))
 
     host_batches = [host_batch(B, 42 + rank * 1000 + i) for i in range(4)]
+    if args.tuning:      # one image (and its latents) repeated over the batch, fresh noise / timesteps per step (:266-281)
+        for hb in host_batches:
+            hb["pixel_values"] = host_batches[0]["pixel_values"][:1].expand(B, -1, -1, -1).contiguous().pin_memory()
+            hb["latents"] = host_batches[0]["latents"][:1].expand(B, -1, -1, -1).contiguous().pin_memory()
     dev_batches = [to_device(hb, device) for hb in host_batches]
     h2d = batch_bytes(host_batches[0])
 
@@ -555,6 +570,8 @@ def main():
                                        "full UNet + loss + bwd + AdamW), random-init, 512^2 (64x64 latents)",
                            "per_gpu_batch": B, "global_batch": B * world, "parallelism": f"dp{world}",
                            "trainable_params": n_train, "cuda_graph": cuda_graph,
+                           "variant": ("domain tuning (configs[3]): all UNet weights trainable, grad clip" if args.tuning else
+                                       "unfreeze_clip_vision" if args.unfreeze_clip_vision else "pretrain (configs[1])"),
                            "l2": "inputs rotate over 4 batches; per-step working set (activations ~30 GB) >> 126 MB L2",
                            "grad_allreduce": "one NCCL all-reduce of the flat fp32 grad arena" if world > 1 else "none"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches,

@@ -35,7 +35,6 @@ struct GemmArgs {
   float alpha;
   int debug;      // E4T_GEMM_DEBUG probes: 1 skip epilogue body, 4 skip output staging, 8 no TMA loads, 16 no MMAs
   int tma_store;  // bf16 output through smem staging + TMA store (coalesced, asynchronous)
-  int poll_ahead; // opt-in: poll the next stage's mbarrier one stage ahead (test_wait)
   int epi_plain;  // default on (E4T_GEMM_EPI_PLAIN=0 disables): separate slab loop for outputs without alpha/bias/rowgroup/residual
 };
 
@@ -92,7 +91,6 @@ e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     {
       int s = 0;
       uint32_t ph = 0;
-      bool pready = false;   // poll of empty_bar[s] issued one stage earlier (see the MMA issuer)
       for (long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int n_t = (int)(t % g.n_tiles);
         long r = t / g.n_tiles;
@@ -110,12 +108,7 @@ e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
           ch0 = (m0 % img) / g.W;
         }
         for (int kc = kc0; kc < kc1; ++kc) {
-          if (!pready) mbar_wait(&empty_bar[s], ph ^ 1u);
-          pready = false;
-          if (g.poll_ahead) {
-            const int ns = (s + 1 == g.stages) ? 0 : s + 1;
-            pready = mbar_test_wait(&empty_bar[ns], ns == 0 ? ph : (ph ^ 1u));
-          }
+          mbar_wait(&empty_bar[s], ph ^ 1u);
           uint8_t* sA = smem + (size_t)s * stage_bytes;
           uint8_t* sB = sA + kATileBytes;
           if (g.debug & 8) {          // probe: no operand traffic at all (MMA + barrier rate on stale smem)
@@ -177,11 +170,9 @@ e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       const uint32_t stage_units = (uint32_t)stage_bytes >> 4;
       int s = 0, as = 0;
       uint32_t ph = 0, aph = 0;
-      // `ready` (opt-in, E4T_GEMM_POLL=1): result of a NON-blocking poll (mbarrier.test_wait) of full_bar[s] issued one
-      // stage earlier, so that the mbarrier round trip of stage s+1 overlaps the tcgen05.mma issues of stage s (probe,
-      // round 2: the issue loop alone — barriers only — costs ~290 clk per k-chunk).  A try_wait here was measured to be
-      // 1.5x SLOWER: it may suspend the thread for a system-defined time when the phase is incomplete.
-      bool ready = false;
+      // (round 2, measured and removed: polling the NEXT stage's mbarrier before issuing the current stage's MMAs — with
+      // try_wait 1.3-1.5x slower (it may suspend the thread), with the non-blocking test_wait 3-7 % slower, and even the
+      // dormant branch cost 5-10 % in this loop; the issue loop itself, barriers only, is ~290 clk per k-chunk)
       for (long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         long r = t / g.n_tiles / g.m_tiles;
         const int sp = (int)(r % g.splits);
@@ -191,12 +182,7 @@ e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)as * 256u;
         for (int kc = kc0; kc < kc1; ++kc) {
-          if (!ready) mbar_wait(&full_bar[s], ph);
-          ready = false;
-          if (g.poll_ahead) {
-            const int ns = (s + 1 == g.stages) ? 0 : s + 1;
-            ready = mbar_test_wait(&full_bar[ns], ns == 0 ? (ph ^ 1u) : ph);
-          }
+          mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           if (elect_one()) {
             const uint64_t da = dA0 + (uint64_t)((uint32_t)s * stage_units);
@@ -502,8 +488,6 @@ static int launch_gemm(const CUtensorMap& mA, const CUtensorMap& mB, GemmArgs& g
   {
     const char* d = getenv("E4T_GEMM_DEBUG");
     g.debug = d ? atoi(d) : 0;
-    const char* pa = getenv("E4T_GEMM_POLL");
-    g.poll_ahead = pa ? atoi(pa) : 0;
     const char* p = getenv("E4T_GEMM_EPI_PLAIN");   // default ON (bit-identical on all 40 step signatures, r02 sweep)
     g.epi_plain = p ? atoi(p) : 1;
   }

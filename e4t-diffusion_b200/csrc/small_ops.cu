@@ -356,57 +356,64 @@ __device__ __forceinline__ float sa_dot(const bf16* a, const bf16* b, int dh) {
   return acc;
 }
 
-// scores + softmax into sP (fp32 [N][kSA_PLD]); returns with sP = P (normalised); row LSE written to lse_out if given
-__device__ __forceinline__ void sa_scores_softmax(float* sP, const bf16* sQ, const bf16* sK, const SmallAttnArgs& a,
-                                                  float* lse_out, const float* lse_in) {
-  const int N = a.N, M = a.M;
-  for (int idx = threadIdx.x; idx < N * M; idx += blockDim.x) {
-    const int i = idx / M, j = idx % M;
+static constexpr int kSA_CH = 32;   // query (fwd, dQ) or key (dK/dV) rows per CTA: blockIdx.z = chunk
+
+// P[i][j] for i in [i0,i1), j in [j0,j1) into sP (row pitch kSA_PLD, indexed [i - i0][j]): softmax over ALL keys when
+// lse == nullptr (forward: the CTA owns whole rows, j0 = 0, j1 = M; the row LSE is written to lse_out), otherwise
+// exp(s - lse[i]) (backward recomputation).  Masked (causal) entries are exactly 0.
+__device__ __forceinline__ void sa_probs(float* sP, const bf16* sQ, const bf16* sK, const SmallAttnArgs& a, int i0, int i1,
+                                         int j0, int j1, float* lse_out, const float* lse) {
+  const int ni = i1 - i0, nj = j1 - j0;
+  for (int idx = threadIdx.x; idx < ni * nj; idx += blockDim.x) {
+    const int i = i0 + idx / nj, j = j0 + idx % nj;
     float s = -INFINITY;
     if (!a.causal || j <= i) s = sa_dot(sQ + i * kSA_LD, sK + j * kSA_LD, a.dh) * a.scale;
-    sP[i * kSA_PLD + j] = s;
+    sP[(i - i0) * kSA_PLD + j] = s;
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int i = warp; i < N; i += nw) {
-    float* row = sP + i * kSA_PLD;
-    float lse;
-    if (lse_in) {
-      lse = lse_in[i];
+  for (int i = i0 + warp; i < i1; i += nw) {
+    float* row = sP + (i - i0) * kSA_PLD;
+    float l;
+    if (lse) {
+      l = lse[i];
     } else {
       float mx = -INFINITY;
-      for (int j = lane; j < M; j += 32) mx = fmaxf(mx, row[j]);
+      for (int j = j0 + lane; j < j1; j += 32) mx = fmaxf(mx, row[j]);
       mx = warp_max(mx);
       float sum = 0.f;
-      for (int j = lane; j < M; j += 32) sum += __expf(row[j] - mx);
+      for (int j = j0 + lane; j < j1; j += 32) sum += __expf(row[j] - mx);
       sum = warp_sum(sum);
-      lse = mx + logf(sum);
-      if (lse_out && lane == 0) lse_out[i] = lse;
+      l = mx + logf(sum);
+      if (lse_out && lane == 0) lse_out[i] = l;
     }
-    for (int j = lane; j < M; j += 32) row[j] = __expf(row[j] - lse);   // masked entries: exp(-inf) = 0
+    for (int j = j0 + lane; j < j1; j += 32) row[j] = __expf(row[j] - l);   // masked entries: exp(-inf) = 0
   }
   __syncthreads();
 }
 
+// forward: CTA = (head, batch, chunk of kSA_CH queries)
 __global__ void __launch_bounds__(256) attn_small_fwd_kernel(const SmallAttnArgs a) {
   extern __shared__ __align__(16) uint8_t sm[];
   bf16* sQ = reinterpret_cast<bf16*>(sm);
   bf16* sK = sQ + kSA_MAX * kSA_LD;
   bf16* sV = sK + kSA_MAX * kSA_LD;
-  float* sP = reinterpret_cast<float*>(sV + kSA_MAX * kSA_LD);
+  float* sP = reinterpret_cast<float*>(sV + kSA_MAX * kSA_LD);   // [kSA_CH][kSA_PLD]
   const int h = blockIdx.x, b = blockIdx.y;
-  sa_load_tile(sQ, a.Q + b * a.q_bs + h * a.dh, a.N, a.dh, a.ldq);
-  sa_load_tile(sK, a.K + b * a.k_bs + h * a.dh, a.M, a.dh, a.ldk);
-  sa_load_tile(sV, a.V + b * a.v_bs + h * a.dh, a.M, a.dh, a.ldv);
+  const int i0 = blockIdx.z * kSA_CH, i1 = min(a.N, i0 + kSA_CH);
+  if (i0 >= a.N) return;
+  const int mk = a.causal ? min(a.M, i1) : a.M;                  // keys this chunk can see
+  sa_load_tile(sQ + i0 * kSA_LD, a.Q + b * a.q_bs + (long long)i0 * a.ldq + h * a.dh, i1 - i0, a.dh, a.ldq);
+  sa_load_tile(sK, a.K + b * a.k_bs + h * a.dh, mk, a.dh, a.ldk);
+  sa_load_tile(sV, a.V + b * a.v_bs + h * a.dh, mk, a.dh, a.ldv);
   __syncthreads();
-  sa_scores_softmax(sP, sQ, sK, a, a.LSE + ((long long)b * a.H + h) * a.N, nullptr);
-  // O[i][d] = sum_j P[i][j] V[j][d]; thread -> (i, pair of d)
+  sa_probs(sP, sQ, sK, a, i0, i1, 0, mk, a.LSE + ((long long)b * a.H + h) * a.N, nullptr);
   const int dp = a.dh / 2;
-  for (int idx = threadIdx.x; idx < a.N * dp; idx += blockDim.x) {
-    const int i = idx / dp, d = (idx % dp) * 2;
-    const float* pr = sP + i * kSA_PLD;
+  for (int idx = threadIdx.x; idx < (i1 - i0) * dp; idx += blockDim.x) {
+    const int i = i0 + idx / dp, d = (idx % dp) * 2;
+    const float* pr = sP + (i - i0) * kSA_PLD;
     float o0 = 0.f, o1 = 0.f;
-    const int jmax = a.causal ? min(a.M, i + 1) : a.M;
+    const int jmax = a.causal ? min(mk, i + 1) : mk;
     for (int j = 0; j < jmax; ++j) {
       const float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(sV + j * kSA_LD + d));
       o0 += pr[j] * v.x;
@@ -416,24 +423,45 @@ __global__ void __launch_bounds__(256) attn_small_fwd_kernel(const SmallAttnArgs
   }
 }
 
+// backward: WHICH = 0 -> dQ, CTA = (head, batch, chunk of kSA_CH queries); WHICH = 1 -> dK and dV, CTA = chunk of keys.
+// Each CTA recomputes its slab of P from the saved LSE (0.4 MFLOP) instead of exchanging partial sums.
+template <int WHICH>
 __global__ void __launch_bounds__(256) attn_small_bwd_kernel(const SmallAttnArgs a) {
   extern __shared__ __align__(16) uint8_t sm[];
   bf16* sQ = reinterpret_cast<bf16*>(sm);
   bf16* sK = sQ + kSA_MAX * kSA_LD;
   bf16* sV = sK + kSA_MAX * kSA_LD;
   bf16* sdO = sV + kSA_MAX * kSA_LD;
-  float* sP = reinterpret_cast<float*>(sdO + kSA_MAX * kSA_LD);
-  float* sdS = sP + kSA_MAX * kSA_PLD;
+  float* sP = reinterpret_cast<float*>(sdO + kSA_MAX * kSA_LD);   // WHICH 0: [kSA_CH][PLD] (rows = my queries);
+  float* sdS = sP + kSA_MAX * kSA_PLD;                            // WHICH 1: [N][PLD] (all queries, my key columns)
   float* sD = sdS + kSA_MAX * kSA_PLD;     // [N] rowsum(dO * O)
   float* sL = sD + kSA_MAX;                // [N] LSE
   const int h = blockIdx.x, b = blockIdx.y;
   const int N = a.N, M = a.M, dh = a.dh;
-  sa_load_tile(sQ, a.Q + b * a.q_bs + h * dh, N, dh, a.ldq);
-  sa_load_tile(sK, a.K + b * a.k_bs + h * dh, M, dh, a.ldk);
-  sa_load_tile(sV, a.V + b * a.v_bs + h * dh, M, dh, a.ldv);
-  sa_load_tile(sdO, a.dO + b * a.do_bs + h * dh, N, dh, a.lddo);
+  int i0, i1, j0, j1;
+  if (WHICH == 0) {
+    i0 = blockIdx.z * kSA_CH; i1 = min(N, i0 + kSA_CH);
+    if (i0 >= N) return;
+    j0 = 0; j1 = a.causal ? min(M, i1) : M;
+  } else {
+    j0 = blockIdx.z * kSA_CH; j1 = min(M, j0 + kSA_CH);
+    if (j0 >= M) return;
+    i0 = a.causal ? j0 : 0; i1 = N;
+    if (i0 >= N) {   // keys no query can see: zero gradients
+      for (int idx = threadIdx.x; idx < (j1 - j0) * (dh / 2); idx += blockDim.x) {
+        const int j = j0 + idx / (dh / 2), d = (idx % (dh / 2)) * 2;
+        *reinterpret_cast<uint32_t*>(a.dK + b * a.dk_bs + (long long)j * a.lddk + h * dh + d) = 0u;
+        *reinterpret_cast<uint32_t*>(a.dV + b * a.dv_bs + (long long)j * a.lddv + h * dh + d) = 0u;
+      }
+      return;
+    }
+  }
+  sa_load_tile(sQ + i0 * kSA_LD, a.Q + b * a.q_bs + (long long)i0 * a.ldq + h * dh, i1 - i0, dh, a.ldq);
+  sa_load_tile(sdO + i0 * kSA_LD, a.dO + b * a.do_bs + (long long)i0 * a.lddo + h * dh, i1 - i0, dh, a.lddo);
+  sa_load_tile(sK + j0 * kSA_LD, a.K + b * a.k_bs + (long long)j0 * a.ldk + h * dh, j1 - j0, dh, a.ldk);
+  sa_load_tile(sV + j0 * kSA_LD, a.V + b * a.v_bs + (long long)j0 * a.ldv + h * dh, j1 - j0, dh, a.ldv);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int i = warp; i < N; i += nw) {   // D_i = sum_d dO[i][d] O[i][d]
+  for (int i = i0 + warp; i < i1; i += nw) {   // D_i = sum_d dO[i][d] O[i][d]
     const bf16* o = a.O + b * a.o_bs + (long long)i * a.ldo + h * dh;
     const bf16* d = a.dO + b * a.do_bs + (long long)i * a.lddo + h * dh;
     float acc = 0.f;
@@ -449,44 +477,46 @@ __global__ void __launch_bounds__(256) attn_small_bwd_kernel(const SmallAttnArgs
     }
   }
   __syncthreads();
-  sa_scores_softmax(sP, sQ, sK, a, nullptr, sL);
+  sa_probs(sP, sQ, sK, a, i0, i1, j0, j1, nullptr, sL);
   // dS[i][j] = P (dP - D) * scale, dP[i][j] = dO[i] . V[j]
-  for (int idx = threadIdx.x; idx < N * M; idx += blockDim.x) {
-    const int i = idx / M, j = idx % M;
-    const float p = sP[i * kSA_PLD + j];
+  const int nj = j1 - j0;
+  for (int idx = threadIdx.x; idx < (i1 - i0) * nj; idx += blockDim.x) {
+    const int i = i0 + idx / nj, j = j0 + idx % nj;
+    const float p = sP[(i - i0) * kSA_PLD + j];
     float ds = 0.f;
     if (p != 0.f) ds = p * (sa_dot(sdO + i * kSA_LD, sV + j * kSA_LD, dh) - sD[i]) * a.scale;
-    sdS[i * kSA_PLD + j] = ds;
+    sdS[(i - i0) * kSA_PLD + j] = ds;
   }
   __syncthreads();
   const int dp = dh / 2;
-  // dQ[i][d] = sum_j dS[i][j] K[j][d]
-  for (int idx = threadIdx.x; idx < N * dp; idx += blockDim.x) {
-    const int i = idx / dp, d = (idx % dp) * 2;
-    const float* r = sdS + i * kSA_PLD;
-    float o0 = 0.f, o1 = 0.f;
-    const int jmax = a.causal ? min(M, i + 1) : M;
-    for (int j = 0; j < jmax; ++j) {
-      const float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(sK + j * kSA_LD + d));
-      o0 += r[j] * v.x;
-      o1 += r[j] * v.y;
+  if (WHICH == 0) {   // dQ[i][d] = sum_j dS[i][j] K[j][d]
+    for (int idx = threadIdx.x; idx < (i1 - i0) * dp; idx += blockDim.x) {
+      const int i = i0 + idx / dp, d = (idx % dp) * 2;
+      const float* r = sdS + (i - i0) * kSA_PLD;
+      float o0 = 0.f, o1 = 0.f;
+      const int jmax = a.causal ? min(j1, i + 1) : j1;
+      for (int j = 0; j < jmax; ++j) {
+        const float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(sK + j * kSA_LD + d));
+        o0 += r[j] * v.x;
+        o1 += r[j] * v.y;
+      }
+      *reinterpret_cast<uint32_t*>(a.dQ + b * a.dq_bs + (long long)i * a.lddq + h * dh + d) = pack_bf16(o0, o1);
     }
-    *reinterpret_cast<uint32_t*>(a.dQ + b * a.dq_bs + (long long)i * a.lddq + h * dh + d) = pack_bf16(o0, o1);
-  }
-  // dK[j][d] = sum_i dS[i][j] Q[i][d];  dV[j][d] = sum_i P[i][j] dO[i][d]
-  for (int idx = threadIdx.x; idx < M * dp; idx += blockDim.x) {
-    const int j = idx / dp, d = (idx % dp) * 2;
-    float k0 = 0.f, k1 = 0.f, v0 = 0.f, v1 = 0.f;
-    const int i0 = a.causal ? j : 0;
-    for (int i = i0; i < N; ++i) {
-      const float ds = sdS[i * kSA_PLD + j], p = sP[i * kSA_PLD + j];
-      const float2 q = unpack_bf16(*reinterpret_cast<const uint32_t*>(sQ + i * kSA_LD + d));
-      const float2 g = unpack_bf16(*reinterpret_cast<const uint32_t*>(sdO + i * kSA_LD + d));
-      k0 += ds * q.x; k1 += ds * q.y;
-      v0 += p * g.x;  v1 += p * g.y;
+  } else {            // dK[j][d] = sum_i dS[i][j] Q[i][d];  dV[j][d] = sum_i P[i][j] dO[i][d]
+    for (int idx = threadIdx.x; idx < nj * dp; idx += blockDim.x) {
+      const int j = j0 + idx / dp, d = (idx % dp) * 2;
+      float k0 = 0.f, k1 = 0.f, v0 = 0.f, v1 = 0.f;
+      const int ia = a.causal ? max(i0, j) : i0;
+      for (int i = ia; i < i1; ++i) {
+        const float ds = sdS[(i - i0) * kSA_PLD + j], p = sP[(i - i0) * kSA_PLD + j];
+        const float2 q = unpack_bf16(*reinterpret_cast<const uint32_t*>(sQ + i * kSA_LD + d));
+        const float2 g = unpack_bf16(*reinterpret_cast<const uint32_t*>(sdO + i * kSA_LD + d));
+        k0 += ds * q.x; k1 += ds * q.y;
+        v0 += p * g.x;  v1 += p * g.y;
+      }
+      *reinterpret_cast<uint32_t*>(a.dK + b * a.dk_bs + (long long)j * a.lddk + h * dh + d) = pack_bf16(k0, k1);
+      *reinterpret_cast<uint32_t*>(a.dV + b * a.dv_bs + (long long)j * a.lddv + h * dh + d) = pack_bf16(v0, v1);
     }
-    *reinterpret_cast<uint32_t*>(a.dK + b * a.dk_bs + (long long)j * a.lddk + h * dh + d) = pack_bf16(k0, k1);
-    *reinterpret_cast<uint32_t*>(a.dV + b * a.dv_bs + (long long)j * a.lddv + h * dh + d) = pack_bf16(v0, v1);
   }
 }
 
@@ -508,13 +538,13 @@ extern "C" int e4t_attn_small_fwd(const void* Q, const void* K, const void* V, v
   a.B = B; a.H = H; a.N = N; a.M = M; a.dh = dh; a.causal = causal;
   a.ldq = ldq; a.q_bs = q_bs; a.ldk = ldk; a.k_bs = k_bs; a.ldv = ldv; a.v_bs = v_bs; a.ldo = ldo; a.o_bs = o_bs;
   a.scale = scale;
-  const size_t smem = (size_t)3 * kSA_MAX * kSA_LD * 2 + (size_t)kSA_MAX * kSA_PLD * 4;
+  const size_t smem = (size_t)3 * kSA_MAX * kSA_LD * 2 + (size_t)kSA_CH * kSA_PLD * 4;
   static bool attr = false;
   if (!attr) {
     E4T_CUDA(cudaFuncSetAttribute(attn_small_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
-  attn_small_fwd_kernel<<<dim3(H, B), 256, smem, (cudaStream_t)stream_>>>(a);
+  attn_small_fwd_kernel<<<dim3(H, B, cdiv(N, kSA_CH)), 256, smem, (cudaStream_t)stream_>>>(a);
   E4T_COUNT_LAUNCH();
   E4T_LAUNCH_CHECK();
   return 0;
@@ -541,10 +571,13 @@ extern "C" int e4t_attn_small_bwd(const void* Q, const void* K, const void* V, c
   const size_t smem = (size_t)4 * kSA_MAX * kSA_LD * 2 + (size_t)2 * kSA_MAX * kSA_PLD * 4 + 2 * kSA_MAX * 4;
   static bool attr = false;
   if (!attr) {
-    E4T_CUDA(cudaFuncSetAttribute(attn_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    E4T_CUDA(cudaFuncSetAttribute(attn_small_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    E4T_CUDA(cudaFuncSetAttribute(attn_small_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
-  attn_small_bwd_kernel<<<dim3(H, B), 256, smem, (cudaStream_t)stream_>>>(a);
+  attn_small_bwd_kernel<0><<<dim3(H, B, cdiv(N, kSA_CH)), 256, smem, (cudaStream_t)stream_>>>(a);
+  E4T_COUNT_LAUNCH();
+  attn_small_bwd_kernel<1><<<dim3(H, B, cdiv(M, kSA_CH)), 256, smem, (cudaStream_t)stream_>>>(a);
   E4T_COUNT_LAUNCH();
   E4T_LAUNCH_CHECK();
   return 0;

@@ -43,6 +43,17 @@ int e4t_gemm_bf16(const void* A, const void* B, void* out, int M, int N, int K, 
 int e4t_conv3x3_bf16(const void* x, const void* w, void* out, int B, int H, int W, int Cin, int Cout, int out_mode,
                      const float* bias, const float* rowgroup, const void* residual, int force_bn, void* stream);
 
+/* 3x3 / stride 2 / pad 1 (diffusers Downsample2D.conv, built at e4t/models/unet_2d_blocks.py:801-808): computed at the
+ * OUTPUT resolution — the implicit-GEMM A operand is gathered with TMA element strides.  x [B][H][W][Cin] ->
+ * out [B][H/2][W/2][Cout]. */
+int e4t_conv3x3_s2_bf16(const void* x, const void* w, void* out, int B, int H, int W, int Cin, int Cout,
+                        const float* bias, int force_bn, void* stream);
+/* Weight gradient of the 3x3 / stride 1 / pad 1 convolution: dw9[tap][co][ci] += sum dy[b][y][x][co] * x[b][y+ky-1][x+kx-1][ci]
+ * (fp32 atomic accumulation; implicit GEMM with 9 taps as the batch dimension, split-K over pixels).  Replaces autograd's
+ * conv2d weight gradient when the base UNet is trainable (tuning_e4t.py:139-146; every requires_grad parameter under
+ * accelerate's DDP, pretrain_e4t.py:410). */
+int e4t_conv3x3_wgrad(const void* x, const void* dy, float* dw9, int B, int H, int W, int Cin, int Cout, void* stream);
+
 /* ---- attention core ------------------------------------------------------------------------------------------ */
 /* O = softmax(Q K^T * scale) V, LSE = logsumexp rows.  Replaces F.scaled_dot_product_attention at
  * e4t/models/cross_attention.py:527-529 (== get_attention_scores + bmm, :222-251,313-315).
@@ -67,6 +78,17 @@ int e4t_attn_bwd_fused(const void* Q, const void* K, const void* V, const void* 
                        long long ldo, long long o_bs, long long lddo, long long do_bs, long long lddq, long long dq_bs,
                        long long lddk, long long dk_bs, long long lddv, long long dv_bs, float scale, void* stream);
 
+/* Short-sequence attention (N, M <= 128, dh <= 64) with optional causal mask: the CLIP text tower's 77-token causal
+ * self-attention (e4t/models/modeling_clip.py:45-51, HF CLIPAttention) and its backward.  Same layout as e4t_attn_fwd. */
+int e4t_attn_small_fwd(const void* Q, const void* K, const void* V, void* O, float* LSE, int B, int H, int N, int M,
+                       int dh, long long ldq, long long q_bs, long long ldk, long long k_bs, long long ldv,
+                       long long v_bs, long long ldo, long long o_bs, float scale, int causal, void* stream);
+int e4t_attn_small_bwd(const void* Q, const void* K, const void* V, const void* O, const void* dO, const float* LSE,
+                       void* dQ, void* dK, void* dV, int B, int H, int N, int M, int dh, long long ldq, long long q_bs,
+                       long long ldk, long long k_bs, long long ldv, long long v_bs, long long ldo, long long o_bs,
+                       long long lddo, long long do_bs, long long lddq, long long dq_bs, long long lddk, long long dk_bs,
+                       long long lddv, long long dv_bs, float scale, int causal, void* stream);
+
 /* ---- normalisation ------------------------------------------------------------------------------------------- */
 /* GroupNorm (+ optional fused SiLU).  Replaces nn.GroupNorm + F.silu in diffusers ResnetBlock2D, Transformer2DModel
  * .norm (transformer_2d.py:149,253) and conv_norm_out/conv_act (unet_2d_condition.py:554-556).
@@ -82,7 +104,27 @@ int e4t_layernorm_fwd(const void* x, const float* gamma, const float* beta, void
 int e4t_layernorm_bwd(const void* x, const void* dy, const float* gamma, const float* stats, void* dx, long long rows,
                       int C, float eps, void* stream);
 
+/* Affine-parameter gradients (accumulating into fp32 dgamma / dbeta), needed when the norms are trainable
+ * (tuning_e4t.py:139-146, --unfreeze_clip_vision).  LayerNorm: stats as written by e4t_layernorm_fwd.  GroupNorm(+SiLU):
+ * mean_c / rstd_c fp32 [B][C] = the group statistics expanded per channel. */
+int e4t_layernorm_param_grad(const void* x, const void* dy, const float* stats, const float* gamma, float* dgamma,
+                             float* dbeta, long long rows, int C, void* stream);
+int e4t_groupnorm_param_grad(const void* x, const void* dy, const float* mean_c, const float* rstd_c, const float* gamma,
+                             const float* beta, float* dgamma, float* dbeta, int B, int HW, int C, int act_silu,
+                             void* stream);
+
 /* ---- elementwise --------------------------------------------------------------------------------------------- */
+/* Activations on bf16: mode 0 exact erf GELU (open_clip ViT MLP, e4t/encoder.py:91-96), 1 quick GELU (HF CLIP text MLP
+ * behind e4t/models/modeling_clip.py:10-82), 2 LeakyReLU(0.01) (E4TEncoder head, e4t/encoder.py:101-105,163-166). */
+int e4t_act_fwd(const void* x, void* y, long long n, int mode, void* stream);
+int e4t_act_bwd(const void* x, const void* dy, void* dx, long long n, int mode, void* stream);
+/* out[g][n] += sum over the rows of group g (rows_per_group consecutive rows; <= 0: one group) of X[m][n]: bias gradients
+ * and the per-image time-embedding-row gradient of ResnetBlock2D. */
+int e4t_colsum_acc(const void* X, float* out, long long M, int N, long long ld, long long rows_per_group, void* stream);
+/* Weight gradients of the UNet's two narrow 3x3 convolutions (conv_in 4->C, unet_2d_condition.py:481; conv_out C->4, :557):
+ * acc[w][n][tap] += sum wide[b][y][x][w] * narrow[b][n][y+sgn*(ky-1)][x+sgn*(kx-1)]; wide bf16 NHWC, narrow fp32 NCHW (<= 4 ch). */
+int e4t_narrow_conv_wgrad(const void* wide, const float* narrow, float* acc, int B, int H, int W, int Cw, int Cn, int sgn,
+                          void* stream);
 /* GEGLU: out = h[:, :F] * gelu(h[:, F:]) (attention.py:409-430). */
 int e4t_geglu_fwd(const void* h, void* out, long long rows, int F, void* stream);
 int e4t_geglu_bwd(const void* h, const void* dout, void* dh, long long rows, int F, void* stream);

@@ -233,3 +233,39 @@ def test_conv3x3_stride2_fwd_bwd(B, H, Cin, Cout):
     assert _rel(y.permute(0, 3, 1, 2), yr) < 6e-3, _rel(y.permute(0, 3, 1, 2), yr)
     assert _rel(x.grad.permute(0, 3, 1, 2), xr.grad) < 6e-3
     assert _rel(conv.weight.grad, wr.grad) < 3e-3 and _rel(conv.bias.grad, br.grad) < 2e-3
+
+
+def test_unfrozen_clip_vision_every_parameter_gradient_vs_oracle():
+    """--unfreeze_clip_vision (README.md:52, pretrain_e4t.py:78,249): every ViT tower weight and every head weight gets
+    its gradient from the e4t kernels; compared with autograd of the fp32 oracle encoder."""
+    from e4t.encoder import E4TEncoder
+    vcfg, W = O.VIT_TINY, 64
+    ucfg = O.TINY_UNET
+    fd = O.pooled_feature_dim(ucfg)
+    sd = O.synth_state_dict(O.encoder_param_shapes(vcfg, fd, W, 129), 51)
+    enc = E4TEncoder(arch="ViT-tiny-test", word_embedding_dim=W, n_odd_layers=129, unet_feature_dim=fd,
+                     freeze_clip_vision=False)
+    enc.load_state_dict(sd)
+    enc = enc.cuda()
+    assert all(p.requires_grad for p in enc.clip_vision.parameters())
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(2, 3, 64, 64, generator=g) * 2 - 1
+    shapes = [(2, 64, 16, 16), (2, 64, 16, 16), (2, 64, 8, 8), (2, 128, 8, 8), (2, 128, 8, 8)]
+    maps = [torch.randn(s, generator=g) for s in shapes]
+    assert sum(s[1] for s in shapes) == fd
+    wout = torch.randn(2, W, generator=g)
+    maps_c = [m.cuda().to(torch.bfloat16).permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2) for m in maps]
+    out = enc(x.cuda(), tuple(maps_c))
+    (out * wout.cuda()).sum().backward()
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ref = O.encoder_forward(sdg, vcfg, x, [m.to(torch.bfloat16).float() for m in maps])
+    (ref * wout).sum().backward()
+    named = dict(enc.named_parameters())
+    assert _rel(out, ref) < 3e-2
+    errs = {k: _rel(named[k].grad, sdg[k].grad) for k in sd if "first_linears" not in k}
+    errs["first_linears(all)"] = _rel(torch.stack([named[f"first_linears.{i}.weight"].grad for i in range(129)]),
+                                     torch.stack([sdg[f"first_linears.{i}.weight"].grad for i in range(129)]))
+    srt = sorted(errs.values())
+    worst = max(errs, key=errs.get)
+    print(f"[unfrozen vit] out {_rel(out, ref):.3e}; {len(errs)} grads: median {srt[len(srt)//2]:.3e} max {srt[-1]:.3e} ({worst})")
+    assert srt[len(srt) // 2] < 3e-2 and srt[-1] < 0.15
