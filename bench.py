@@ -573,7 +573,13 @@ def main():
                            "variant": ("domain tuning (configs[3]): all UNet weights trainable, grad clip" if args.tuning else
                                        "unfreeze_clip_vision" if args.unfreeze_clip_vision else "pretrain (configs[1])"),
                            "l2": "inputs rotate over 4 batches; per-step working set (activations ~30 GB) >> 126 MB L2",
-                           "grad_allreduce": "one NCCL all-reduce of the flat fp32 grad arena" if world > 1 else "none"},
+                           "grad_allreduce": ("NCCL all-reduce of the flat fp32 grad arena: encoder-head slice issued from "
+                                              "inside backward on a comm stream (overlaps the enc-half UNet backward), "
+                                              "WeightOffsets slice after backward; "
+                                              + ("all inside the CUDA graph" if getattr(step, "_graph_has_opt", False)
+                                                 else "eager after the compute-only graph")
+                                              + ("; " + step._capture_note if getattr(step, "_capture_note", None) else ""))
+                           if world > 1 else "none"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
                 "gpu_launches_per_step": launches // max(args.steps, 1), "loss": loss, "roofline": roof, "kernels": micro,
                 "cpu_baseline": cpu}

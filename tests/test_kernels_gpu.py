@@ -197,3 +197,34 @@ def test_attention_fused_qkv_strides():
     oref, _ = _attn_ref(q.float(), k.float(), v.float(), H)
     o, _ = ops.attn_fwd(q, k, v, H)
     assert _rel(o, oref) < 6e-3
+
+
+def test_fp32_output_kernels_meet_1e3_at_baseline_shapes():
+    """north_star's tolerance (1e-3 relative, fp32) per kernel at BASELINE shapes, where the kernel can write fp32: the
+    tcgen05 GEMM and the implicit-GEMM convolution with fp32 outputs, and the attention core's fp32 output (LSE).  Inputs
+    are bf16-representable, the reference is fp64 torch.  (bf16 OUTPUTS carry 2^-9 rounding by themselves; the attention
+    O tensor is therefore compared with the reference ROUNDED to bf16, which isolates the kernel's own error.)"""
+    from e4t_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(123)
+    # QKV projection GEMM of level 0 at B=16: (65536, 320) x (960, 320)^T
+    A = _mk((65536, 320), g, 1.0)
+    W = _mk((960, 320), g, 0.05)
+    y = ops.gemm(A, W, out_dtype=torch.float32)
+    ref = A[:8192].double() @ W.double().t()
+    e_gemm = _rel(y[:8192], ref)
+    # ResnetBlock conv 320 -> 320 at 64x64, B=4
+    x = _mk((4, 64, 64, 320), g, 1.0)
+    w = torch.randn(320, 320, 3, 3, generator=g, device="cuda") * 0.02
+    w9 = w.permute(2, 3, 0, 1).reshape(9, 320, 320).to(torch.bfloat16).contiguous()
+    yc = ops.conv3x3(x, w9, out_dtype=torch.float32)
+    refc = F.conv2d(x[:1].double().permute(0, 3, 1, 2), w9.double().view(3, 3, 320, 320).permute(2, 3, 0, 1), padding=1)
+    e_conv = _rel(yc[:1].permute(0, 3, 1, 2), refc)
+    # level-0 self-attention (N = M = 4096, 8 x 40), B=2
+    q, k, v = _mk((2, 4096, 320), g), _mk((2, 4096, 320), g), _mk((2, 4096, 320), g)
+    o, lse = ops.attn_fwd(q, k, v, 8)
+    oref, lse_ref = _attn_ref(q.float(), k.float(), v.float(), 8)
+    e_lse = ((lse - lse_ref).abs() / lse_ref.abs().clamp_min(1.0)).max().item()
+    e_o = _rel(o.float(), oref.to(torch.bfloat16).float())
+    print(f"[fp32 outputs] gemm {e_gemm:.2e}  conv {e_conv:.2e}  attention LSE {e_lse:.2e}  attention O vs bf16(ref) {e_o:.2e}")
+    assert e_gemm < 1e-3 and e_conv < 1e-3 and e_lse < 1e-3
+    assert e_o < 4e-3
