@@ -585,8 +585,19 @@ def main():
                 "cpu_baseline": cpu}
         print(json.dumps(line))
     if world > 1:
+        sys.stdout.flush()
         dist.barrier()      # rank 0 may still be timing kernels for the roofline object; leave together
+        # A CUDA graph that holds captured NCCL kernels keeps the communicator busy: destroying the process group while the
+        # graph is alive hung the 2-GPU run at exit (r02 call 9: JSON line printed, then no exit).  Drop the graph first;
+        # the timer is the backstop so that a teardown problem can never turn a finished measurement into a time-out.
+        step.release_cuda_graph()
+        torch.cuda.synchronize()
+        import threading
+        t = threading.Timer(60.0, lambda: os._exit(0))
+        t.daemon = True
+        t.start()
         dist.destroy_process_group()
+        t.cancel()
 
 
 if __name__ == "__main__":

@@ -390,6 +390,274 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
   }
 }
 
+// =============================================================================================
+// Double-buffered S (attn_fwd3_kernel): two 128-query tiles, each with TWO score buffers in TMEM.
+//   TMEM  S_t,b [ (2t+b) BKV, .. ) | O_t [4 BKV + t dpad, ..)            2 (2 BKV + dpad) <= 512  ->  BKV = 96 for dpad <= 64
+// The tensor core computes S_t(j+2) right after P_t(j)·V_j, i.e. TWO blocks ahead of the softmax, so the softmax warps
+// of a tile run block after block without ever waiting for S (in attn_fwd2_kernel S_t(j+1) can only be issued after
+// P_t(j) exists: the softmax warps waited 31 % of the time for it, and the MUFU pipe idled 45 %).  The only remaining
+// softmax -> tensor -> softmax dependency is the (rare) rescale of O, which waits for P_t(j-1)·V on its own barrier.
+// P_t(j) overwrites the first BKV/2 columns of S_t,(j&1); S_t(j+2) is issued after P_t(j)·V_j and the tensor pipe
+// executes in order, so it cannot overwrite P_t(j) early.
+// =============================================================================================
+template <int BKV>
+__global__ void __launch_bounds__(384, 1)
+attn_fwd3_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                 const __grid_constant__ CUtensorMap mapV, const AttnArgs a) {
+  constexpr int NP = BKV / 2;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int q_bytes = a.DC * 16384;
+  const int kv_chunk = BKV * 128;
+  const int kv_tile = a.DC * kv_chunk;
+  uint8_t* sQ = smem;                             // [2 tiles][DC][128][64]
+  uint8_t* sK = sQ + 2 * q_bytes;                 // [kst][DC][BKV][64]
+  uint8_t* sV = sK + a.kst * kv_tile;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + a.kst * kv_tile);
+  uint64_t* q_full = bars;            // [1]
+  uint64_t* k_full = bars + 1;        // [4]
+  uint64_t* k_empty = k_full + 4;     // [4]
+  uint64_t* v_full = k_empty + 4;     // [4]
+  uint64_t* v_empty = v_full + 4;     // [4]
+  uint64_t* s_full = v_empty + 4;     // [2 tiles][2 buffers]  MMA -> softmax t : S_t(j) complete in buffer j & 1
+  uint64_t* p_ready = s_full + 4;     // [2]  softmax t -> MMA : P_t(j) written (and O_t rescaled)
+  uint64_t* pv_done = p_ready + 2;    // [2]  MMA -> softmax t : P_t(j) V retired (only consulted before a rescale / at the end)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 256, h = blockIdx.y, b = blockIdx.z;
+
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&p_ready[i], 128);
+      mbar_init(&pv_done[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapQ);
+    tma_prefetch_desc(&mapK);
+    tma_prefetch_desc(&mapV);
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tO0 = tmem + (uint32_t)(4 * BKV);
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      mbar_expect_tx(q_full, (uint32_t)(2 * q_bytes));
+      for (int t = 0; t < 2; ++t)
+        for (int c = 0; c < a.DC; ++c) tma_load_4d(sQ + t * q_bytes + c * 16384, &mapQ, q_full, c * 64, h, q0 + 128 * t, b);
+    }
+    // K runs two blocks ahead of V (S is computed two blocks ahead): K(0), K(1), then V(j), K(j+2) per block
+    for (int step = 0; step < a.nblk + 2; ++step) {
+      const int jk = step, jv = step - 2;
+      if (jk < a.nblk) {
+        const int st = jk % a.kst;
+        mbar_wait(&k_empty[st], (uint32_t)(((jk / a.kst) & 1) ^ 1));
+        if (elect_one()) {
+          mbar_expect_tx(&k_full[st], (uint32_t)kv_tile);
+          for (int c = 0; c < a.DC; ++c)
+            tma_load_4d(sK + st * kv_tile + c * kv_chunk, &mapK, &k_full[st], c * 64, h, jk * BKV, b);
+        }
+      }
+      if (jv >= 0) {
+        const int st = jv % a.kst;
+        mbar_wait(&v_empty[st], (uint32_t)(((jv / a.kst) & 1) ^ 1));
+        if (elect_one()) {
+          mbar_expect_tx(&v_full[st], (uint32_t)kv_tile);
+          for (int c = 0; c < a.DC; ++c)
+            tma_load_4d(sV + st * kv_tile + c * kv_chunk, &mapV, &v_full[st], c * 64, h, jv * BKV, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc_s = umma_idesc_bf16((uint32_t)BKV, false, false);
+    const uint32_t idesc_o = umma_idesc_bf16((uint32_t)a.dpad, false, true);
+    mbar_wait(q_full, 0);
+    // prologue: S_t(0) and S_t(1)
+    for (int jj = 0; jj < 2 && jj < a.nblk; ++jj) {
+      const int st = jj % a.kst;
+      mbar_wait(&k_full[st], (uint32_t)((jj / a.kst) & 1));
+      tc_fence_after();
+      if (elect_one()) {
+        for (int t = 0; t < 2; ++t) {
+          mma_kmajor(tmem + (uint32_t)((2 * t + jj) * BKV), smem_u32(sQ + t * q_bytes), 16384, smem_u32(sK + st * kv_tile),
+                     kv_chunk, a.dh, a.DC, idesc_s);
+          if (t == 1) umma_commit(&k_empty[st]);
+          umma_commit(&s_full[2 * t + jj]);
+        }
+      }
+      __syncwarp();
+    }
+    for (int j = 0; j < a.nblk; ++j) {
+      const int st = j % a.kst;
+      const int jn = j + 2, stn = jn % a.kst;
+      const bool more = jn < a.nblk;
+      for (int t = 0; t < 2; ++t) {
+        mbar_wait(&p_ready[t], (uint32_t)(j & 1));
+        if (t == 0) {
+          mbar_wait(&v_full[st], (uint32_t)((j / a.kst) & 1));
+          if (more) mbar_wait(&k_full[stn], (uint32_t)((jn / a.kst) & 1));
+        }
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t tS = tmem + (uint32_t)((2 * t + (j & 1)) * BKV);
+          mma_pv_ts(tO0 + (uint32_t)(t * a.dpad), tS, smem_u32(sV + st * kv_tile), kv_chunk, BKV, idesc_o, j > 0 ? 1u : 0u);
+          if (t == 1) umma_commit(&v_empty[st]);
+          umma_commit(&pv_done[t]);
+          if (more) {
+            mma_kmajor(tS, smem_u32(sQ + t * q_bytes), 16384, smem_u32(sK + stn * kv_tile), kv_chunk, a.dh, a.DC, idesc_s);
+            if (t == 1) umma_commit(&k_empty[stn]);
+            umma_commit(&s_full[2 * t + (j & 1)]);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== softmax warps: tile t = (warp - 4) / 4, one query row per thread =====================
+    const int t = (warp - 4) >> 2;
+    const int ew = warp & 3;
+    const int row = ew * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(ew * 32) << 16;
+    const uint32_t tO = tO0 + (uint32_t)(t * a.dpad) + lane_base;
+    const float sl2 = a.scale * kLog2e;
+    const u64 sl2_2 = f2_pack(sl2, sl2);
+    const int ochunk = a.dpad >> 4;
+    float m = -INFINITY;
+    float l0 = 0.f, l1 = 0.f;
+    for (int j = 0; j < a.nblk; ++j) {
+      const uint32_t tS = tmem + (uint32_t)((2 * t + (j & 1)) * BKV) + lane_base;
+      mbar_wait(&s_full[2 * t + (j & 1)], (uint32_t)((j >> 1) & 1));
+      tc_fence_after();
+      uint32_t v[BKV];
+#pragma unroll
+      for (int c = 0; c < BKV; c += 32) tmem_ld32(tS + (uint32_t)c, v + c);
+      tmem_ld_wait();
+      const int kv0 = j * BKV;
+      if (kv0 + BKV > a.M) {
+#pragma unroll
+        for (int e = 0; e < BKV; ++e)
+          if (kv0 + e >= a.M) v[e] = 0xff800000u;
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int e = 0; e < BKV; e += 4) {
+        mx0 = max3(mx0, __uint_as_float(v[e]), __uint_as_float(v[e + 1]));
+        mx1 = max3(mx1, __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+      }
+      const float mx = fmaxf(mx0, mx1);
+      const bool need = (mx - m) * sl2 > 8.f;
+      if (__any_sync(0xffffffffu, need)) {
+        const float m_new = need ? mx : m;
+        const float alpha = ex2_approx((m - m_new) * sl2);
+        l0 *= alpha;
+        l1 *= alpha;
+        m = m_new;
+        if (j > 0) {
+          mbar_wait(&pv_done[t], (uint32_t)((j - 1) & 1));   // O_t must hold P V of every block < j
+          tc_fence_after();
+          for (int oc = 0; oc < ochunk; ++oc) {
+            uint32_t ov[16];
+            tmem_ld16(tO + (uint32_t)(oc * 16), ov);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) ov[e] = __float_as_uint(__uint_as_float(ov[e]) * alpha);
+            tmem_st16(tO + (uint32_t)(oc * 16), ov);
+          }
+        }
+      }
+      const float nmb = -m * sl2;
+      const u64 nmb2 = f2_pack(nmb, nmb);
+      u64 ls = f2_pack(0.f, 0.f), ls2 = f2_pack(0.f, 0.f);
+      constexpr int kLag = 6, kLead = 4;
+      u64 xq[NP];
+#pragma unroll
+      for (int e = 0; e < kLead; ++e)
+        xq[e] = f2_fma(f2_pack(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1])), sl2_2, nmb2);
+#pragma unroll
+      for (int e = 0; e < NP + kLag; ++e) {
+        if (e < NP) {
+          float x0, x1, p0, p1;
+          f2_unpack(xq[e], x0, x1);
+          asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(x0));
+          if (e + kLead < NP)
+            xq[e + kLead] = f2_fma(f2_pack(__uint_as_float(v[2 * (e + kLead)]), __uint_as_float(v[2 * (e + kLead) + 1])),
+                                   sl2_2, nmb2);
+          asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(x1));
+          xq[e] = f2_pack(p0, p1);
+        }
+        if (e >= kLag) {
+          const int c = e - kLag;
+          if (c & 1) ls2 = f2_add(ls2, xq[c]);
+          else ls = f2_add(ls, xq[c]);
+          float p0, p1;
+          f2_unpack(xq[c], p0, p1);
+          v[c] = pack_bf16(p0, p1);
+        }
+      }
+      {
+        float s0, s1;
+        f2_unpack(f2_add(ls, ls2), s0, s1);
+        l0 += s0;
+        l1 += s1;
+      }
+      // P_t(j) -> TMEM columns [0, BKV/2) of S_t,(j&1)
+      tmem_st32(tS, v);
+      if constexpr (NP > 32) tmem_st16(tS + 32u, v + 32);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&p_ready[t]);
+    }
+    // ---- epilogue ----
+    mbar_wait(&pv_done[t], (uint32_t)((a.nblk - 1) & 1));
+    tc_fence_after();
+    const float lt = l0 + l1;
+    const float inv_l = 1.f / lt;
+    const int n = q0 + 128 * t + row;
+    for (int oc = 0; oc < ochunk; ++oc) {
+      const int c = oc * 16;
+      uint32_t ov[16];
+      tmem_ld16(tO + (uint32_t)c, ov);
+      tmem_ld_wait();
+      if (n < a.N) {
+        bf16* o = a.O + (long long)b * a.o_bs + (long long)n * a.ldo + h * a.dh + c;
+#pragma unroll
+        for (int i = 0; i < 16; i += 8) {
+          if (c + i < a.dh) {
+            *reinterpret_cast<uint4*>(o + i) =
+                make_uint4(pack_bf16(__uint_as_float(ov[i]) * inv_l, __uint_as_float(ov[i + 1]) * inv_l),
+                           pack_bf16(__uint_as_float(ov[i + 2]) * inv_l, __uint_as_float(ov[i + 3]) * inv_l),
+                           pack_bf16(__uint_as_float(ov[i + 4]) * inv_l, __uint_as_float(ov[i + 5]) * inv_l),
+                           pack_bf16(__uint_as_float(ov[i + 6]) * inv_l, __uint_as_float(ov[i + 7]) * inv_l));
+          }
+        }
+      }
+    }
+    if (n < a.N) a.LSE[((long long)b * a.H + h) * a.N + n] = m * a.scale + logf(lt);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Host
 // ---------------------------------------------------------------------------------------------
@@ -416,18 +684,45 @@ int e4t_attn_fwd2_try(const void* Q, const void* K, const void* V, void* O, floa
                       long long ldq, long long q_bs, long long ldk, long long k_bs, long long ldv, long long v_bs,
                       long long ldo, long long o_bs, float scale, cudaStream_t st) {
   // E4T_ATTN_FWD2: "0" disables this kernel; otherwise a string of flags: 'p<k>' FMA-pipe exp2 for k of every 8 pairs,
-  // 'f' select the <4 tiles x 64 keys> shape (measured slower, see below), 'n' no exp-phase token
+  // 'f' select the <4 tiles x 64 keys> shape (measured slower, see below), 'n' no exp-phase token,
+  // 'd' the double-buffered-S kernel attn_fwd3_kernel (dh <= 64)
   const char* e = getenv("E4T_ATTN_FWD2");
-  int poly8 = 0, wide = 1, token = 1;
+  int poly8 = 0, wide = 1, token = 1, dbuf = 0;
   if (e) {
     if (e[0] == '0' && e[1] == 0) return 0;
     for (const char* c = e; *c; ++c) {
       if (*c == 'p' && c[1] >= '0' && c[1] <= '7') poly8 = c[1] - '0';
       if (*c == 'f') wide = 0;
       if (*c == 'n') token = 0;
+      if (*c == 'd') dbuf = 1;
     }
   }
   if (dh > 128 || M < 128 || N < 128) return 0;
+  if (dbuf && dh <= 64 && M >= 192) {   // attn_fwd3_kernel<96>: two S buffers per tile, 96-key blocks
+    AttnArgs a;
+    memset(&a, 0, sizeof(a));
+    a.B = B; a.H = H; a.N = N; a.M = M; a.dh = dh;
+    a.DC = 1;
+    a.dpad = (dh + 15) / 16 * 16;
+    a.BKV = 96;
+    a.nblk = cdiv(M, 96);
+    a.kst = 4;
+    a.scale = scale;
+    a.O = (bf16*)O; a.ldo = ldo; a.o_bs = o_bs; a.LSE = LSE;
+    const size_t smem = (size_t)2 * 16384 + (size_t)2 * 4 * 96 * 128 + 512 + 1024;
+    CUtensorMap mQ, mK, mV;
+    if (e4t_attn_make_head_map(&mQ, Q, dh, H, N, B, ldq, q_bs, 128)) return -1;
+    if (e4t_attn_make_head_map(&mK, K, dh, H, M, B, ldk, k_bs, 96)) return -1;
+    if (e4t_attn_make_head_map(&mV, V, dh, H, M, B, ldv, v_bs, 96)) return -1;
+    static bool attr3 = false;
+    if (!attr3) {
+      if (cudaFuncSetAttribute(attn_fwd3_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+        return -1;
+      attr3 = true;
+    }
+    attn_fwd3_kernel<96><<<dim3(cdiv(N, 256), H, B), 384, smem, st>>>(mQ, mK, mV, a);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+  }
   AttnArgs a;
   memset(&a, 0, sizeof(a));
   a.B = B; a.H = H; a.N = N; a.M = M; a.dh = dh;

@@ -298,6 +298,18 @@ class PretrainStep:
         self._graph = graph
         return self
 
+    def release_cuda_graph(self):
+        """Drop the captured step (and its static buffers).  Call before `dist.destroy_process_group()`: a live graph
+        with captured NCCL kernels keeps the communicator referenced and the destroy waits for it."""
+        self._graph = None
+        self._static_out = None
+        self._static = None
+        self._drop_autograd_refs()
+        import gc
+        gc.collect()
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+
     def _drop_autograd_refs(self):
         if self.wo_bank is not None:
             self.wo_bank.drop_autograd_refs()
