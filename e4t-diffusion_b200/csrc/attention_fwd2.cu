@@ -420,8 +420,11 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
   uint64_t* v_full = k_empty + 4;     // [4]
   uint64_t* v_empty = v_full + 4;     // [4]
   uint64_t* s_full = v_empty + 4;     // [2 tiles][2 buffers]  MMA -> softmax t : S_t(j) complete in buffer j & 1
-  uint64_t* p_ready = s_full + 4;     // [2]  softmax t -> MMA : P_t(j) written (and O_t rescaled)
-  uint64_t* pv_done = p_ready + 2;    // [2]  MMA -> softmax t : P_t(j) V retired (only consulted before a rescale / at the end)
+  uint64_t* p_ready = s_full + 4;     // [2 tiles][2 buffers]  softmax t -> MMA : P_t(j) written (and O_t rescaled).  One
+                                      // barrier per S buffer: a softmax warp group can be TWO blocks ahead of the MMA warp
+                                      // (S_t(j+1) exists while the MMA warp still waits for the other tile's P(j-1)), and a
+                                      // parity wait only tolerates a lead of one phase (a single barrier deadlocked, r02 call 10)
+  uint64_t* pv_done = p_ready + 4;    // [2]  MMA -> softmax t : P_t(j) V retired (only consulted before a rescale / at the end)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -435,11 +438,9 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
-    }
-    for (int i = 0; i < 2; ++i) {
       mbar_init(&p_ready[i], 128);
-      mbar_init(&pv_done[i], 1);
     }
+    for (int i = 0; i < 2; ++i) mbar_init(&pv_done[i], 1);
     fence_mbar_init();
   }
   if (warp == 0 && lane == 0) {
@@ -508,7 +509,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
       const int jn = j + 2, stn = jn % a.kst;
       const bool more = jn < a.nblk;
       for (int t = 0; t < 2; ++t) {
-        mbar_wait(&p_ready[t], (uint32_t)(j & 1));
+        mbar_wait(&p_ready[2 * t + (j & 1)], (uint32_t)((j >> 1) & 1));
         if (t == 0) {
           mbar_wait(&v_full[st], (uint32_t)((j / a.kst) & 1));
           if (more) mbar_wait(&k_full[stn], (uint32_t)((jn / a.kst) & 1));
@@ -621,7 +622,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
       if constexpr (NP > 32) tmem_st16(tS + 32u, v + 32);
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&p_ready[t]);
+      mbar_arrive(&p_ready[2 * t + (j & 1)]);
     }
     // ---- epilogue ----
     mbar_wait(&pv_done[t], (uint32_t)((a.nblk - 1) & 1));

@@ -46,7 +46,7 @@ static constexpr int kCSlabs = 4;  // output staging slabs (8 KiB each) for the 
 
 __global__ void __launch_bounds__(kThreads, 1)
 e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                const __grid_constant__ CUtensorMap mapC, const __grid_constant__ CUtensorMap mapC32, const GemmArgs g) {
+                const __grid_constant__ CUtensorMap mapC, const GemmArgs g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // align dynamic smem to 1024 B (SWIZZLE_128B atoms)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -170,6 +170,8 @@ e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       const uint32_t stage_units = (uint32_t)stage_bytes >> 4;
       int s = 0, as = 0;
       uint32_t ph = 0, aph = 0;
+      // (round 2, measured and removed: per-WARP output staging with 32x32 TMA stores instead of 128-thread slabs, no
+      // CTA-level barrier in the slab loop — 65536x960x320 49.9 us vs 48.3 us, 65536x320x320 21.6 vs 20.1 us, r02 call 10)
       // (round 2, measured and removed: polling the NEXT stage's mbarrier before issuing the current stage's MMAs — with
       // try_wait 1.3-1.5x slower (it may suspend the thread), with the non-blocking test_wait 3-7 % slower, and even the
       // dormant branch cost 5-10 % in this loop; the issue loop itself, barriers only, is ~290 clk per k-chunk)
@@ -244,38 +246,6 @@ e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
           __syncwarp();
           tmem_ld32(t_row + (uint32_t)c, v);
         }
-        if (g.epi_plain == 2) {
-          // per-WARP staging and stores: every warp owns two 2 KiB buffers ([32 rows][64 B], SWIZZLE_64B) and issues its
-          // own 32x32 TMA stores, so the slab loop has no CTA-level barrier at all (the 128-thread version below pays two
-          // bar.sync per 32-column slab; with ~600-clk TMEM loads under MMA load the epilogue of a 128x256 tile, 3.3 us,
-          // was longer than a K = 320 mainloop, 2.1 us)
-          const uint32_t swl = ((uint32_t)lane >> 1) & 3u;
-          for (; c < g.BN && n0 + c < g.N; c += 64) {
-            tmem_ld_wait();
-            uint32_t w[16];
-#pragma unroll
-            for (int q = 0; q < 16; ++q) w[q] = pack_bf16(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1]));
-            const int cn = c + 64;
-            if (cn < g.BN && n0 + cn < g.N) {
-              __syncwarp();
-              tmem_ld32(t_row + (uint32_t)cn, v);
-            }
-            uint8_t* wbuf = stage_c + (((warp - 4) * 2 + (int)(slab_ctr & 1)) << 11);
-            if (elect_one()) tma_store_wait_read<1>();   // this warp's store that last read the buffer has drained
-            __syncwarp();
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              *reinterpret_cast<uint4*>(wbuf + lane * 64 + ((((uint32_t)q) ^ swl) << 4)) =
-                  make_uint4(w[q * 4], w[q * 4 + 1], w[q * 4 + 2], w[q * 4 + 3]);
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (elect_one()) {
-              tma_store_3d(&mapC32, wbuf, n0 + c, m_t * kBM + ew * 32, bz);
-              tma_store_commit();
-            }
-            ++slab_ctr;
-          }
-        } else
         for (; c < g.BN && n0 + c < g.N; c += 64) {
           tmem_ld_wait();
           uint32_t w[16];
@@ -452,7 +422,7 @@ e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       as ^= 1;
       if (as == 0) aph ^= 1u;
     }
-    if (g.tma_store && (warp == 4 || warp == 8 || g.epi_plain == 2)) {
+    if (g.tma_store && (warp == 4 || warp == 8)) {
       if (elect_one()) tma_store_wait_all();  // smem must outlive the stores (same lane that committed them)
     }
   }
@@ -514,15 +484,14 @@ static int pick_bn(int N, long m_tiles_x_batch, bool b_mn, int force_bn, int kch
 
 static int launch_gemm(const CUtensorMap& mA, const CUtensorMap& mB, GemmArgs& g, cudaStream_t stream) {
   // output map for the TMA-store epilogue: bf16 [batch][M][N], box 32 cols x 128 rows, SWIZZLE_64B
-  CUtensorMap mC, mC32;
+  CUtensorMap mC;
   memset(&mC, 0, sizeof(mC));
-  memset(&mC32, 0, sizeof(mC32));
   g.tma_store = 0;
   {
     const char* d = getenv("E4T_GEMM_DEBUG");
     g.debug = d ? atoi(d) : 0;
     const char* p = getenv("E4T_GEMM_EPI_PLAIN");   // default ON (bit-identical on all 40 step signatures, r02 sweep)
-    g.epi_plain = p ? atoi(p) : 1;   // 0 general loop, 1 plain loop (128-thread slabs), 2 plain loop with per-warp stores
+    g.epi_plain = p ? atoi(p) : 1;
   }
   static int use_tma_store = -1;
   if (use_tma_store < 0) {
@@ -535,8 +504,6 @@ static int launch_gemm(const CUtensorMap& mA, const CUtensorMap& mB, GemmArgs& g
     uint64_t str[2] = {(uint64_t)g.ldo * 2, (uint64_t)(g.batch > 1 ? g.out_bstride : (long long)g.M * g.ldo) * 2};
     uint32_t box[3] = {32, kBM, 1};
     if (int e = e4t_tmap_encode(&mC, g.out, 3, dims, str, box, 2, 64)) return e;
-    uint32_t box32[3] = {32, 32, 1};
-    if (int e = e4t_tmap_encode(&mC32, g.out, 3, dims, str, box32, 2, 64)) return e;
     g.tma_store = 1;
   }
   const int stage_bytes = kATileBytes + g.BN * kBK * 2;
@@ -553,7 +520,7 @@ static int launch_gemm(const CUtensorMap& mA, const CUtensorMap& mB, GemmArgs& g
   const long total = (long)g.batch * g.splits * g.m_tiles * g.n_tiles;
   int grid = (int)(total < num_sms() ? total : num_sms());
   if (grid < 1) return 0;
-  e4t_gemm_kernel<<<grid, kThreads, smem, stream>>>(mA, mB, mC, mC32, g);
+  e4t_gemm_kernel<<<grid, kThreads, smem, stream>>>(mA, mB, mC, g);
   E4T_COUNT_LAUNCH();
   E4T_LAUNCH_CHECK();
   return 0;

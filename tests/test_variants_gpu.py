@@ -107,8 +107,5 @@ def test_gemm_plain_epilogue_is_bit_identical(M, N, K, b_mn):
     y1 = ops.gemm(A, Bm, b_mn=b_mn)
     os.environ["E4T_GEMM_EPI_PLAIN"] = "0"
     y0 = ops.gemm(A, Bm, b_mn=b_mn)
-    os.environ["E4T_GEMM_EPI_PLAIN"] = "2"       # per-warp 32x32 TMA stores
-    y2 = ops.gemm(A, Bm, b_mn=b_mn)
     torch.cuda.synchronize()
     assert torch.equal(y0, y1)
-    assert torch.equal(y0, y2)
