@@ -425,7 +425,10 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
                                       // (S_t(j+1) exists while the MMA warp still waits for the other tile's P(j-1)), and a
                                       // parity wait only tolerates a lead of one phase (a single barrier deadlocked, r02 call 10)
   uint64_t* pv_done = p_ready + 4;    // [2]  MMA -> softmax t : P_t(j) V retired (only consulted before a rescale / at the end)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+  uint64_t* o_done = pv_done + 2;     // [2]  MMA -> softmax t : the LAST P_t V retired.  Not pv_done: after its last block a
+                                      // softmax group may be two P·V behind the tensor core, three possible phase counts alias
+                                      // under a parity wait (the epilogue read O early: right LSE, wrong O; r02 call 12)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 256, h = blockIdx.y, b = blockIdx.z;
@@ -440,7 +443,10 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
       mbar_init(&s_full[i], 1);
       mbar_init(&p_ready[i], 128);
     }
-    for (int i = 0; i < 2; ++i) mbar_init(&pv_done[i], 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&pv_done[i], 1);
+      mbar_init(&o_done[i], 1);
+    }
     fence_mbar_init();
   }
   if (warp == 0 && lane == 0) {
@@ -520,6 +526,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
           mma_pv_ts(tO0 + (uint32_t)(t * a.dpad), tS, smem_u32(sV + st * kv_tile), kv_chunk, BKV, idesc_o, j > 0 ? 1u : 0u);
           if (t == 1) umma_commit(&v_empty[st]);
           umma_commit(&pv_done[t]);
+          if (j == a.nblk - 1) umma_commit(&o_done[t]);
           if (more) {
             mma_kmajor(tS, smem_u32(sQ + t * q_bytes), 16384, smem_u32(sK + stn * kv_tile), kv_chunk, a.dh, a.DC, idesc_s);
             if (t == 1) umma_commit(&k_empty[stn]);
@@ -625,7 +632,7 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
       mbar_arrive(&p_ready[2 * t + (j & 1)]);
     }
     // ---- epilogue ----
-    mbar_wait(&pv_done[t], (uint32_t)((a.nblk - 1) & 1));
+    mbar_wait(&o_done[t], 0);
     tc_fence_after();
     const float lt = l0 + l1;
     const float inv_l = 1.f / lt;
