@@ -967,63 +967,92 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
                  tdQ = tdK + (uint32_t)a.dpad;
   const uint32_t tPT = tdQ + (uint32_t)a.dpad;   // PT: Pᵀ as bf16 pairs, 64 columns (256 + 3*dpad + 64 <= 512)
 
-  if (warp == 0) {   // whole warp runs the control flow, one elected lane issues (see attn_fwd_kernel)
-    {
-      if (elect_one()) {
-        mbar_expect_tx(kv_full, (uint32_t)(2 * kv_bytes));
-        for (int c = 0; c < a.DC; ++c) {
-          tma_load_4d(sK + c * 16384, &mapK, kv_full, c * 64, h, k0, b);
-          tma_load_4d(sV + c * 16384, &mapV, kv_full, c * 64, h, k0, b);
-        }
+  // Both role warps run their loops in ONE elected thread, with every shared-memory descriptor built once outside the
+  // loop and the ring stage / phase tracked incrementally (round 2: the per-block `j % kst`, `j / kst` and 60 descriptor
+  // constructions sat on the critical path — the thread phase and the tensor phase of a block do not overlap here, so the
+  // time this thread needs to ISSUE the 30 MMAs of a block adds to every block).
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_expect_tx(kv_full, (uint32_t)(2 * kv_bytes));
+      for (int c = 0; c < a.DC; ++c) {
+        tma_load_4d(sK + c * 16384, &mapK, kv_full, c * 64, h, k0, b);
+        tma_load_4d(sV + c * 16384, &mapV, kv_full, c * 64, h, k0, b);
       }
+      int st = 0;
+      uint32_t ph = 0;
       for (int j = 0; j < a.nblk; ++j) {
-        const int st = j % a.kst;
-        mbar_wait(&q_empty[st], (uint32_t)(((j / a.kst) & 1) ^ 1));
-        if (elect_one()) {
-          mbar_expect_tx(&q_full[st], (uint32_t)(2 * q_tile));
-          for (int c = 0; c < a.DC; ++c) {
-            tma_load_4d(sQ + st * q_tile + c * BQ * 128, &mapQ, &q_full[st], c * 64, h, j * BQ, b);
-            tma_load_4d(sdO + st * q_tile + c * BQ * 128, &mapdO, &q_full[st], c * 64, h, j * BQ, b);
-          }
+        mbar_wait(&q_empty[st], ph ^ 1u);
+        mbar_expect_tx(&q_full[st], (uint32_t)(2 * q_tile));
+        for (int c = 0; c < a.DC; ++c) {
+          tma_load_4d(sQ + st * q_tile + c * BQ * 128, &mapQ, &q_full[st], c * 64, h, j * BQ, b);
+          tma_load_4d(sdO + st * q_tile + c * BQ * 128, &mapdO, &q_full[st], c * 64, h, j * BQ, b);
+        }
+        if (++st == a.kst) {
+          st = 0;
+          ph ^= 1u;
         }
       }
     }
   } else if (warp == 1) {
-    {
+    if (elect_one()) {
       const uint32_t idesc_s = umma_idesc_bf16((uint32_t)BQ, false, false);
       const uint32_t idesc_o = umma_idesc_bf16((uint32_t)a.dpad, false, true);
       const uint32_t idesc_q = umma_idesc_bf16((uint32_t)a.dpad, true, true);
+      // descriptor bases (start-address field in 16-byte units; every tile is 1024-byte aligned and all of shared memory
+      // is below 256 KiB, so adding an offset never carries out of the 14-bit field)
+      //   K-major tile, k-step kk of dh:            + (kk >> 2) * 1024 + (kk & 3) * 2     (64-wide chunks of 16 KiB)
+      //   MN-major tile, 16-row step ks:            + ks * 128
+      const uint64_t dK_k = umma_desc(smem_u32(sK), 16, 1024);          // A of S^T  = K Q^T
+      const uint64_t dV_k = umma_desc(smem_u32(sV), 16, 1024);          // A of dP^T = V dO^T
+      const uint64_t dK_mn = umma_desc(smem_u32(sK), 16384, 1024);      // B of dQ   = dS K
+      const uint64_t dST_k = umma_desc(smem_u32(sdST), 16, 1024);       // A of dK  += dS^T Q
+      const uint64_t dST_mn = umma_desc(smem_u32(sdST), 16384, 1024);   // A of dQ
+      const uint64_t dPT_k = umma_desc(smem_u32(sPT), 16, 1024);        // A of dV  += P^T dO   (!PT)
+      const uint64_t dQ_k0 = umma_desc(smem_u32(sQ), 16, 1024), ddO_k0 = umma_desc(smem_u32(sdO), 16, 1024);
+      const uint64_t dQ_mn0 = umma_desc(smem_u32(sQ), BQ * 128, 1024), ddO_mn0 = umma_desc(smem_u32(sdO), BQ * 128, 1024);
+      const uint32_t q_units = (uint32_t)q_tile >> 4;
+      const int ksteps = (a.dh + 15) >> 4;
       mbar_wait(kv_full, 0);
+      int st = 0;
+      uint32_t ph = 0;
       for (int j = 0; j < a.nblk; ++j) {
-        const int st = j % a.kst;
-        mbar_wait(&q_full[st], (uint32_t)((j / a.kst) & 1));
+        const uint64_t so = (uint64_t)((uint32_t)st * q_units);
+        mbar_wait(&q_full[st], ph);
         tc_fence_after();
-        if (elect_one()) {
-          mma_kmajor(tST, smem_u32(sK), 16384, smem_u32(sQ + st * q_tile), BQ * 128, a.dh, a.DC, idesc_s);
-          mma_kmajor(tdPT, smem_u32(sV), 16384, smem_u32(sdO + st * q_tile), BQ * 128, a.dh, a.DC, idesc_s);
-          umma_commit(sp_full);
+        for (int kk = 0; kk < ksteps; ++kk) {
+          const uint64_t off = (uint64_t)(((kk >> 2) << 10) + ((kk & 3) << 1));
+          umma_bf16(tST, dK_k + off, dQ_k0 + so + off, idesc_s, kk > 0 ? 1u : 0u);
         }
+        for (int kk = 0; kk < ksteps; ++kk) {
+          const uint64_t off = (uint64_t)(((kk >> 2) << 10) + ((kk & 3) << 1));
+          umma_bf16(tdPT, dV_k + off, ddO_k0 + so + off, idesc_s, kk > 0 ? 1u : 0u);
+        }
+        umma_commit(sp_full);
         mbar_wait(ds_ready, (uint32_t)(j & 1));
         tc_fence_after();
-        if (elect_one()) {
-          if constexpr (PT) {
-            for (int ks = 0; ks < BQ / 16; ++ks)   // A = Pᵀ[:, 16 ks .. 16 ks + 16) = 8 TMEM columns
-              umma_bf16_ts(tdV, tPT + (uint32_t)(ks * 8), umma_desc(smem_u32(sdO + st * q_tile) + ks * 2048, BQ * 128, 1024),
-                           idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
-          } else {
-            mma_pv(tdV, smem_u32(sPT), smem_u32(sdO + st * q_tile), BQ * 128, BQ, idesc_o, j > 0 ? 1u : 0u);
-          }
-          mma_pv(tdK, smem_u32(sdST), smem_u32(sQ + st * q_tile), BQ * 128, BQ, idesc_o, j > 0 ? 1u : 0u);
+#pragma unroll
+        for (int ks = 0; ks < BQ / 16; ++ks) {   // dV += P^T dO: A = P^T[:, 16 ks .. 16 ks + 16)
+          const uint32_t acc = (j > 0 || ks > 0) ? 1u : 0u;
+          if constexpr (PT) umma_bf16_ts(tdV, tPT + (uint32_t)(ks * 8), ddO_mn0 + so + (uint64_t)(ks * 128), idesc_o, acc);
+          else umma_bf16(tdV, dPT_k + (uint64_t)(((ks >> 2) << 10) + ((ks & 3) << 1)), ddO_mn0 + so + (uint64_t)(ks * 128), idesc_o, acc);
         }
+#pragma unroll
+        for (int ks = 0; ks < BQ / 16; ++ks)     // dK += dS^T Q
+          umma_bf16(tdK, dST_k + (uint64_t)(((ks >> 2) << 10) + ((ks & 3) << 1)), dQ_mn0 + so + (uint64_t)(ks * 128), idesc_o,
+                    (j > 0 || ks > 0) ? 1u : 0u);
         if (j > 0) {
           mbar_wait(dq_empty, (uint32_t)((j - 1) & 1));  // threads have drained dQ_blk of block j-1
           tc_fence_after();
         }
-        if (elect_one()) {
-          mma_ds_k(tdQ, smem_u32(sdST), smem_u32(sK), 16384, idesc_q);
-          umma_commit(&q_empty[st]);
-          umma_commit(dq_full);
-          umma_commit(acc_done);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)           // dQ_blk = dS K
+          umma_bf16(tdQ, dST_mn + (uint64_t)(ks * 128), dK_mn + (uint64_t)(ks * 128), idesc_q, ks > 0 ? 1u : 0u);
+        umma_commit(&q_empty[st]);
+        umma_commit(dq_full);
+        umma_commit(acc_done);
+        if (++st == a.kst) {
+          st = 0;
+          ph ^= 1u;
         }
       }
     }

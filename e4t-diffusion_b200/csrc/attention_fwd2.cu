@@ -157,68 +157,89 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
   const uint32_t tmem = *tmem_slot;
   const uint32_t tO0 = tmem + (uint32_t)(NT * BKV);
 
+  // Both role warps run their loops in ONE elected thread with descriptors built once and the ring stage / phase tracked
+  // incrementally (see attn_fwd3_kernel: the issue rate of the MMA thread is on the critical path).
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
       mbar_expect_tx(q_full, (uint32_t)(NT * q_bytes));
       for (int t = 0; t < NT; ++t)
         for (int c = 0; c < a.DC; ++c) tma_load_4d(sQ + t * q_bytes + c * 16384, &mapQ, q_full, c * 64, h, q0 + 128 * t, b);
-    }
-    for (int j = 0; j < a.nblk; ++j) {
-      const int st = j % a.kst;
-      const uint32_t ph = (uint32_t)((j / a.kst) & 1);
-      mbar_wait(&k_empty[st], ph ^ 1u);
-      if (elect_one()) {
+      int st = 0;
+      uint32_t ph = 0;
+      for (int j = 0; j < a.nblk; ++j) {
+        mbar_wait(&k_empty[st], ph ^ 1u);
         mbar_expect_tx(&k_full[st], (uint32_t)kv_tile);
         for (int c = 0; c < a.DC; ++c)
           tma_load_4d(sK + st * kv_tile + c * kv_chunk, &mapK, &k_full[st], c * 64, h, j * BKV, b);
-      }
-      mbar_wait(&v_empty[st], ph ^ 1u);
-      if (elect_one()) {
+        mbar_wait(&v_empty[st], ph ^ 1u);
         mbar_expect_tx(&v_full[st], (uint32_t)kv_tile);
         for (int c = 0; c < a.DC; ++c)
           tma_load_4d(sV + st * kv_tile + c * kv_chunk, &mapV, &v_full[st], c * 64, h, j * BKV, b);
+        if (++st == a.kst) {
+          st = 0;
+          ph ^= 1u;
+        }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    const uint32_t idesc_s = umma_idesc_bf16((uint32_t)BKV, false, false);
-    const uint32_t idesc_o = umma_idesc_bf16((uint32_t)a.dpad, false, true);
-    mbar_wait(q_full, 0);
-    mbar_wait(&k_full[0], 0);
-    tc_fence_after();
     if (elect_one()) {
+      const uint32_t idesc_s = umma_idesc_bf16((uint32_t)BKV, false, false);
+      const uint32_t idesc_o = umma_idesc_bf16((uint32_t)a.dpad, false, true);
+      // descriptor bases in 16-byte units: Q tile t: + t * (q_bytes >> 4); k-step kk of dh: chunk (kk >> 2), 32 B * (kk & 3)
+      const uint64_t dQ0 = umma_desc(smem_u32(sQ), 16, 1024);
+      const uint64_t dK0 = umma_desc(smem_u32(sK), 16, 1024);
+      const uint64_t dV0 = umma_desc(smem_u32(sV), (uint32_t)kv_chunk, 1024);
+      const uint32_t q_units = (uint32_t)q_bytes >> 4, stage_u = (uint32_t)kv_tile >> 4, kchunk_u = (uint32_t)kv_chunk >> 4;
+      const int ksteps = (a.dh + 15) >> 4;
+      auto issue_qk = [&](uint32_t tS, int t, uint64_t dK) {
+        for (int kk = 0; kk < ksteps; ++kk)
+          umma_bf16(tS, dQ0 + (uint64_t)((uint32_t)t * q_units + (uint32_t)(kk >> 2) * 1024u + (uint32_t)(kk & 3) * 2u),
+                    dK + (uint64_t)((uint32_t)(kk >> 2) * kchunk_u + (uint32_t)(kk & 3) * 2u), idesc_s, kk > 0 ? 1u : 0u);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
       for (int t = 0; t < NT; ++t) {
-        mma_kmajor(tmem + (uint32_t)(t * BKV), smem_u32(sQ + t * q_bytes), 16384, smem_u32(sK), kv_chunk, a.dh, a.DC,
-                   idesc_s);
+        issue_qk(tmem + (uint32_t)(t * BKV), t, dK0);
         if (t == NT - 1) umma_commit(&k_empty[0]);
         umma_commit(&s_full[t]);
       }
-    }
-    for (int j = 0; j < a.nblk; ++j) {
-      const int st = j % a.kst;
-      const int jn = j + 1, stn = jn % a.kst;
-      const bool more = jn < a.nblk;
-      for (int t = 0; t < NT; ++t) {
-        mbar_wait(&p_ready[t], (uint32_t)(j & 1));
-        if (t == 0) {
-          mbar_wait(&v_full[st], (uint32_t)((j / a.kst) & 1));
-          if (more) mbar_wait(&k_full[stn], (uint32_t)((jn / a.kst) & 1));
-        }
-        tc_fence_after();
-        if (elect_one()) {
+      int st = 0, stn = a.kst > 1 ? 1 : 0;
+      uint32_t ph = 0, phn = a.kst > 1 ? 0u : 1u;     // stage / phase of block j and of block j + 1
+      for (int j = 0; j < a.nblk; ++j) {
+        const bool more = j + 1 < a.nblk;
+        const uint64_t dV = dV0 + (uint64_t)((uint32_t)st * stage_u);
+        const uint64_t dK = dK0 + (uint64_t)((uint32_t)stn * stage_u);
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          mbar_wait(&p_ready[t], (uint32_t)(j & 1));
+          if (t == 0) {
+            mbar_wait(&v_full[st], ph);
+            if (more) mbar_wait(&k_full[stn], phn);
+          }
+          tc_fence_after();
           const uint32_t tS = tmem + (uint32_t)(t * BKV);
-          mma_pv_ts(tO0 + (uint32_t)(t * a.dpad), tS, smem_u32(sV + st * kv_tile), kv_chunk, BKV, idesc_o, j > 0 ? 1u : 0u);
+          const uint32_t tO = tO0 + (uint32_t)(t * a.dpad);
+#pragma unroll
+          for (int ks = 0; ks < BKV / 16; ++ks)
+            umma_bf16_ts(tO, tS + (uint32_t)(ks * 8), dV + (uint64_t)(ks * 128), idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
           if (t == NT - 1) umma_commit(&v_empty[st]);
           if (more) {
-            mma_kmajor(tS, smem_u32(sQ + t * q_bytes), 16384, smem_u32(sK + stn * kv_tile), kv_chunk, a.dh, a.DC, idesc_s);
+            issue_qk(tS, t, dK);
             if (t == NT - 1) umma_commit(&k_empty[stn]);
             umma_commit(&s_full[t]);
           } else {
             umma_commit(&o_done[t]);
           }
         }
-        __syncwarp();
+        st = stn;
+        ph = phn;
+        if (++stn == a.kst) {
+          stn = 0;
+          phn ^= 1u;
+        }
       }
     }
   } else if (warp >= 4) {
@@ -461,79 +482,87 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
   const uint32_t tmem = *tmem_slot;
   const uint32_t tO0 = tmem + (uint32_t)(4 * BKV);
 
+  // The two role warps run their whole loop in ONE elected thread, with a compile-time ring depth and descriptors
+  // precomputed outside the loop: the first version (whole-warp control flow, `j % a.kst`, descriptors rebuilt per k-step)
+  // executed ~700 instructions per block pair in the MMA warp, and ncu showed that warp BUSY (not waiting) while the
+  // softmax warps waited a third of their time for S — the issue rate of this one thread is on the critical path.
+  constexpr int KST = 4;
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
       mbar_expect_tx(q_full, (uint32_t)(2 * q_bytes));
-      for (int t = 0; t < 2; ++t)
-        for (int c = 0; c < a.DC; ++c) tma_load_4d(sQ + t * q_bytes + c * 16384, &mapQ, q_full, c * 64, h, q0 + 128 * t, b);
-    }
-    // K runs two blocks ahead of V (S is computed two blocks ahead): K(0), K(1), then V(j), K(j+2) per block
-    for (int step = 0; step < a.nblk + 2; ++step) {
-      const int jk = step, jv = step - 2;
-      if (jk < a.nblk) {
-        const int st = jk % a.kst;
-        mbar_wait(&k_empty[st], (uint32_t)(((jk / a.kst) & 1) ^ 1));
-        if (elect_one()) {
+      for (int t = 0; t < 2; ++t) tma_load_4d(sQ + t * q_bytes, &mapQ, q_full, 0, h, q0 + 128 * t, b);
+      // K runs two blocks ahead of V (S is computed two blocks ahead): K(0), K(1), then K(j+2), V(j) per block
+      const int nsteps = a.nblk + 2;
+      for (int step = 0; step < nsteps; ++step) {
+        if (step < a.nblk) {
+          const int st = step & (KST - 1);
+          mbar_wait(&k_empty[st], (uint32_t)(((step >> 2) & 1) ^ 1));
           mbar_expect_tx(&k_full[st], (uint32_t)kv_tile);
-          for (int c = 0; c < a.DC; ++c)
-            tma_load_4d(sK + st * kv_tile + c * kv_chunk, &mapK, &k_full[st], c * 64, h, jk * BKV, b);
+          tma_load_4d(sK + st * kv_tile, &mapK, &k_full[st], 0, h, step * BKV, b);
         }
-      }
-      if (jv >= 0) {
-        const int st = jv % a.kst;
-        mbar_wait(&v_empty[st], (uint32_t)(((jv / a.kst) & 1) ^ 1));
-        if (elect_one()) {
+        const int jv = step - 2;
+        if (jv >= 0) {
+          const int st = jv & (KST - 1);
+          mbar_wait(&v_empty[st], (uint32_t)(((jv >> 2) & 1) ^ 1));
           mbar_expect_tx(&v_full[st], (uint32_t)kv_tile);
-          for (int c = 0; c < a.DC; ++c)
-            tma_load_4d(sV + st * kv_tile + c * kv_chunk, &mapV, &v_full[st], c * 64, h, jv * BKV, b);
+          tma_load_4d(sV + st * kv_tile, &mapV, &v_full[st], 0, h, jv * BKV, b);
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    const uint32_t idesc_s = umma_idesc_bf16((uint32_t)BKV, false, false);
-    const uint32_t idesc_o = umma_idesc_bf16((uint32_t)a.dpad, false, true);
-    mbar_wait(q_full, 0);
-    // prologue: S_t(0) and S_t(1)
-    for (int jj = 0; jj < 2 && jj < a.nblk; ++jj) {
-      const int st = jj % a.kst;
-      mbar_wait(&k_full[st], (uint32_t)((jj / a.kst) & 1));
-      tc_fence_after();
-      if (elect_one()) {
+    if (elect_one()) {
+      const uint32_t idesc_s = umma_idesc_bf16((uint32_t)BKV, false, false);
+      const uint32_t idesc_o = umma_idesc_bf16((uint32_t)a.dpad, false, true);
+      const int ksteps = (a.dh + 15) >> 4;                              // dh <= 64: one 64-wide chunk
+      const uint64_t dQ0 = umma_desc(smem_u32(sQ), 16, 1024);           // tile t: + t * (16384 >> 4); k-step k: + 2 k
+      const uint64_t dK0 = umma_desc(smem_u32(sK), 16, 1024);           // stage s: + s * stage_u
+      const uint64_t dV0 = umma_desc(smem_u32(sV), (uint32_t)kv_chunk, 1024);   // 16-key step ks: + ks * (2048 >> 4)
+      const uint32_t stage_u = (uint32_t)kv_tile >> 4;
+      mbar_wait(q_full, 0);
+      // prologue: S_t(0) and S_t(1)
+      for (int jj = 0; jj < 2 && jj < a.nblk; ++jj) {
+        mbar_wait(&k_full[jj], 0);
+        tc_fence_after();
         for (int t = 0; t < 2; ++t) {
-          mma_kmajor(tmem + (uint32_t)((2 * t + jj) * BKV), smem_u32(sQ + t * q_bytes), 16384, smem_u32(sK + st * kv_tile),
-                     kv_chunk, a.dh, a.DC, idesc_s);
-          if (t == 1) umma_commit(&k_empty[st]);
+          const uint32_t tS = tmem + (uint32_t)((2 * t + jj) * BKV);
+          for (int k = 0; k < ksteps; ++k)
+            umma_bf16(tS, dQ0 + (uint64_t)(t * 1024 + 2 * k), dK0 + (uint64_t)(jj * stage_u + 2 * k), idesc_s, k > 0);
+          if (t == 1) umma_commit(&k_empty[jj]);
           umma_commit(&s_full[2 * t + jj]);
         }
       }
-      __syncwarp();
-    }
-    for (int j = 0; j < a.nblk; ++j) {
-      const int st = j % a.kst;
-      const int jn = j + 2, stn = jn % a.kst;
-      const bool more = jn < a.nblk;
-      for (int t = 0; t < 2; ++t) {
-        mbar_wait(&p_ready[2 * t + (j & 1)], (uint32_t)((j >> 1) & 1));
-        if (t == 0) {
-          mbar_wait(&v_full[st], (uint32_t)((j / a.kst) & 1));
-          if (more) mbar_wait(&k_full[stn], (uint32_t)((jn / a.kst) & 1));
-        }
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t tS = tmem + (uint32_t)((2 * t + (j & 1)) * BKV);
-          mma_pv_ts(tO0 + (uint32_t)(t * a.dpad), tS, smem_u32(sV + st * kv_tile), kv_chunk, BKV, idesc_o, j > 0 ? 1u : 0u);
+      for (int j = 0; j < a.nblk; ++j) {
+        const int st = j & (KST - 1), b01 = j & 1;
+        const int jn = j + 2, stn = jn & (KST - 1);
+        const bool more = jn < a.nblk;
+        const uint32_t ph2 = (uint32_t)((j >> 1) & 1);
+        const uint64_t dV = dV0 + (uint64_t)((uint32_t)st * stage_u);
+        const uint64_t dK = dK0 + (uint64_t)((uint32_t)stn * stage_u);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(&p_ready[2 * t + b01], ph2);
+          if (t == 0) {
+            mbar_wait(&v_full[st], (uint32_t)((j >> 2) & 1));
+            if (more) mbar_wait(&k_full[stn], (uint32_t)((jn >> 2) & 1));
+          }
+          tc_fence_after();
+          const uint32_t tS = tmem + (uint32_t)((2 * t + b01) * BKV);
+          const uint32_t tO = tO0 + (uint32_t)(t * a.dpad);
+#pragma unroll
+          for (int ks = 0; ks < BKV / 16; ++ks)
+            umma_bf16_ts(tO, tS + (uint32_t)(ks * 8), dV + (uint64_t)(ks * 128), idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
           if (t == 1) umma_commit(&v_empty[st]);
           umma_commit(&pv_done[t]);
           if (j == a.nblk - 1) umma_commit(&o_done[t]);
           if (more) {
-            mma_kmajor(tS, smem_u32(sQ + t * q_bytes), 16384, smem_u32(sK + stn * kv_tile), kv_chunk, a.dh, a.DC, idesc_s);
+            for (int k = 0; k < ksteps; ++k)
+              umma_bf16(tS, dQ0 + (uint64_t)(t * 1024 + 2 * k), dK + (uint64_t)(2 * k), idesc_s, k > 0);
             if (t == 1) umma_commit(&k_empty[stn]);
-            umma_commit(&s_full[2 * t + (j & 1)]);
+            umma_commit(&s_full[2 * t + b01]);
           }
         }
-        __syncwarp();
       }
     }
   } else if (warp >= 4) {
