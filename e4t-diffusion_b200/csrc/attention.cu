@@ -1013,12 +1013,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
       const uint32_t q_units = (uint32_t)q_tile >> 4;
       const int ksteps = (a.dh + 15) >> 4;
       mbar_wait(kv_full, 0);
-      int st = 0;
-      uint32_t ph = 0;
-      for (int j = 0; j < a.nblk; ++j) {
-        const uint64_t so = (uint64_t)((uint32_t)st * q_units);
-        mbar_wait(&q_full[st], ph);
-        tc_fence_after();
+      auto issue_s_dp = [&](uint64_t so) {      // S^T = K Q^T and dP^T = V dO^T of the block whose {Q, dO} stage starts at `so`
         for (int kk = 0; kk < ksteps; ++kk) {
           const uint64_t off = (uint64_t)(((kk >> 2) << 10) + ((kk & 3) << 1));
           umma_bf16(tST, dK_k + off, dQ_k0 + so + off, idesc_s, kk > 0 ? 1u : 0u);
@@ -1028,6 +1023,30 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
           umma_bf16(tdPT, dV_k + off, ddO_k0 + so + off, idesc_s, kk > 0 ? 1u : 0u);
         }
         umma_commit(sp_full);
+      };
+      // REORDERED issue (PT, two {Q, dO} stages): S^T / dP^T of block j+1 are issued right after dV(j), BEFORE dK(j) and
+      // dQ(j), so the threads start block j+1 after ~920 clk of tensor work instead of ~2000 and dK / dQ of block j run
+      // under their arithmetic.  dS^T is double buffered for this (block parity; the second buffer is the P^T tile that
+      // PT leaves unused); P^T in TMEM needs no second buffer: the threads write P^T(j+1) only after S^T(j+1) is complete,
+      // which the in-order tensor pipe executes after dV(j), the reader of P^T(j).
+      const bool reord = PT && a.kst == 2 && a.sbuf;
+      const uint64_t dST2_k = umma_desc(smem_u32(sPT), 16, 1024), dST2_mn = umma_desc(smem_u32(sPT), 16384, 1024);
+      int st = 0;
+      uint32_t ph = 0;
+      if (reord) {
+        mbar_wait(&q_full[0], 0);
+        tc_fence_after();
+        issue_s_dp(0);
+      }
+      for (int j = 0; j < a.nblk; ++j) {
+        const uint64_t so = (uint64_t)((uint32_t)st * q_units);
+        const bool second = reord && (j & 1);
+        const uint64_t dSk = second ? dST2_k : dST_k, dSmn = second ? dST2_mn : dST_mn;
+        if (!reord) {
+          mbar_wait(&q_full[st], ph);
+          tc_fence_after();
+          issue_s_dp(so);
+        }
         mbar_wait(ds_ready, (uint32_t)(j & 1));
         tc_fence_after();
 #pragma unroll
@@ -1036,17 +1055,23 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
           if constexpr (PT) umma_bf16_ts(tdV, tPT + (uint32_t)(ks * 8), ddO_mn0 + so + (uint64_t)(ks * 128), idesc_o, acc);
           else umma_bf16(tdV, dPT_k + (uint64_t)(((ks >> 2) << 10) + ((ks & 3) << 1)), ddO_mn0 + so + (uint64_t)(ks * 128), idesc_o, acc);
         }
+        if (reord && j + 1 < a.nblk) {
+          const int stn = st ^ 1;
+          mbar_wait(&q_full[stn], stn == 0 ? (ph ^ 1u) : ph);   // block j+1: next stage; the phase flips when it wraps to 0
+          tc_fence_after();
+          issue_s_dp((uint64_t)((uint32_t)stn * q_units));
+        }
 #pragma unroll
         for (int ks = 0; ks < BQ / 16; ++ks)     // dK += dS^T Q
-          umma_bf16(tdK, dST_k + (uint64_t)(((ks >> 2) << 10) + ((ks & 3) << 1)), dQ_mn0 + so + (uint64_t)(ks * 128), idesc_o,
-                    (j > 0 || ks > 0) ? 1u : 0u);
+          umma_bf16(tdK, dSk + (uint64_t)(((ks >> 2) << 10) + ((ks & 3) << 1)), dQ_mn0 + so + (uint64_t)(ks * 128),
+                    idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
         if (j > 0) {
           mbar_wait(dq_empty, (uint32_t)((j - 1) & 1));  // threads have drained dQ_blk of block j-1
           tc_fence_after();
         }
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks)           // dQ_blk = dS K
-          umma_bf16(tdQ, dST_mn + (uint64_t)(ks * 128), dK_mn + (uint64_t)(ks * 128), idesc_q, ks > 0 ? 1u : 0u);
+          umma_bf16(tdQ, dSmn + (uint64_t)(ks * 128), dK_mn + (uint64_t)(ks * 128), idesc_q, ks > 0 ? 1u : 0u);
         umma_commit(&q_empty[st]);
         umma_commit(dq_full);
         umma_commit(acc_done);
@@ -1166,7 +1191,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
 #pragma unroll
           for (int e = 0; e < 8; ++e) wp[e] = wd[e] = 0u;
         }
-        uint8_t* pd = sdST + (c >> 6) * 16384 + rowoff;
+        uint8_t* pd = ((PT && a.kst == 2 && a.sbuf && (j & 1)) ? sPT : sdST) + (c >> 6) * 16384 + rowoff;
         const uint32_t cb = (uint32_t)((c & 63) >> 3);
         if constexpr (PT) {
           __syncwarp();
@@ -1487,6 +1512,10 @@ extern "C" int e4t_attn_bwd_fused(const void* Q, const void* K, const void* V, c
   // opt-in: Pᵀ through TMEM (256 + 3*dpad + 64 columns must fit 512: dpad <= 64)
   const char* pte = getenv("E4T_ATTN_PT_TMEM");
   const bool pt_tmem = (!pte || atoi(pte) != 0) && 256 + 3 * dpad + 64 <= 512;   // default ON
+  {   // (field reused) 1 = reordered MMA issue with double-buffered dS^T (default; E4T_ATTN_BWD_REORD=0 keeps the block order)
+    const char* re = getenv("E4T_ATTN_BWD_REORD");
+    a.sbuf = (!re || atoi(re) != 0) ? 1 : 0;
+  }
   CUtensorMap mDQ;
   memset(&mDQ, 0, sizeof(mDQ));
   if (dq_tma) {

@@ -421,7 +421,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
 // P_t(j) overwrites the first BKV/2 columns of S_t,(j&1); S_t(j+2) is issued after P_t(j)·V_j and the tensor pipe
 // executes in order, so it cannot overwrite P_t(j) early.
 // =============================================================================================
-template <int BKV>
+template <int BKV, int POLY8>
 __global__ void __launch_bounds__(384, 1)
 attn_fwd3_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                  const __grid_constant__ CUtensorMap mapV, const AttnArgs a) {
@@ -622,29 +622,53 @@ attn_fwd3_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
       const u64 nmb2 = f2_pack(nmb, nmb);
       u64 ls = f2_pack(0.f, 0.f), ls2 = f2_pack(0.f, 0.f);
       constexpr int kLag = 6, kLead = 4;
-      u64 xq[NP];
+      if constexpr (POLY8 != 0) {
+        // exp2 of POLY8 pairs out of every 8 on the FMA pipe (exp2_poly2): with S double-buffered the MUFU pipe is ~70 %
+        // busy, so moving a share of the exponentials off it shortens the phase (it did not while the kernel waited for S)
 #pragma unroll
-      for (int e = 0; e < kLead; ++e)
-        xq[e] = f2_fma(f2_pack(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1])), sl2_2, nmb2);
-#pragma unroll
-      for (int e = 0; e < NP + kLag; ++e) {
-        if (e < NP) {
-          float x0, x1, p0, p1;
-          f2_unpack(xq[e], x0, x1);
-          asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(x0));
-          if (e + kLead < NP)
-            xq[e + kLead] = f2_fma(f2_pack(__uint_as_float(v[2 * (e + kLead)]), __uint_as_float(v[2 * (e + kLead) + 1])),
-                                   sl2_2, nmb2);
-          asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(x1));
-          xq[e] = f2_pack(p0, p1);
-        }
-        if (e >= kLag) {
-          const int c = e - kLag;
-          if (c & 1) ls2 = f2_add(ls2, xq[c]);
-          else ls = f2_add(ls, xq[c]);
+        for (int e = 0; e < NP; ++e) {
+          const u64 x2 = f2_fma(f2_pack(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1])), sl2_2, nmb2);
+          u64 p2;
+          if ((e & 7) < POLY8) {
+            p2 = exp2_poly2(x2);
+          } else {
+            float x0, x1, p0, p1;
+            f2_unpack(x2, x0, x1);
+            asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(x0));
+            asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(x1));
+            p2 = f2_pack(p0, p1);
+          }
           float p0, p1;
-          f2_unpack(xq[c], p0, p1);
-          v[c] = pack_bf16(p0, p1);
+          f2_unpack(p2, p0, p1);
+          v[e] = pack_bf16(p0, p1);
+          if (e & 1) ls2 = f2_add(ls2, p2);
+          else ls = f2_add(ls, p2);
+        }
+      } else {
+        u64 xq[NP];
+#pragma unroll
+        for (int e = 0; e < kLead; ++e)
+          xq[e] = f2_fma(f2_pack(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1])), sl2_2, nmb2);
+#pragma unroll
+        for (int e = 0; e < NP + kLag; ++e) {
+          if (e < NP) {
+            float x0, x1, p0, p1;
+            f2_unpack(xq[e], x0, x1);
+            asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(p0) : "f"(x0));
+            if (e + kLead < NP)
+              xq[e + kLead] = f2_fma(f2_pack(__uint_as_float(v[2 * (e + kLead)]), __uint_as_float(v[2 * (e + kLead) + 1])),
+                                     sl2_2, nmb2);
+            asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(p1) : "f"(x1));
+            xq[e] = f2_pack(p0, p1);
+          }
+          if (e >= kLag) {
+            const int c = e - kLag;
+            if (c & 1) ls2 = f2_add(ls2, xq[c]);
+            else ls = f2_add(ls, xq[c]);
+            float p0, p1;
+            f2_unpack(xq[c], p0, p1);
+            v[c] = pack_bf16(p0, p1);
+          }
         }
       }
       {
@@ -720,11 +744,13 @@ static int launch_fwd2(const CUtensorMap& mQ, const CUtensorMap& mK, const CUten
 int e4t_attn_fwd2_try(const void* Q, const void* K, const void* V, void* O, float* LSE, int B, int H, int N, int M, int dh,
                       long long ldq, long long q_bs, long long ldk, long long k_bs, long long ldv, long long v_bs,
                       long long ldo, long long o_bs, float scale, cudaStream_t st) {
-  // E4T_ATTN_FWD2: "0" disables this kernel; otherwise a string of flags: 'p<k>' FMA-pipe exp2 for k of every 8 pairs,
-  // 'f' select the <4 tiles x 64 keys> shape (measured slower, see below), 'n' no exp-phase token,
-  // 'd' the double-buffered-S kernel attn_fwd3_kernel (dh <= 64)
+  // E4T_ATTN_FWD2: "0" disables these kernels (single-tile attn_fwd_kernel); otherwise a string of flags:
+  //   'd' / 's'  force the double-buffered-S kernel attn_fwd3_kernel (default where it applies: dh <= 64, M >= 192) /
+  //              the single-buffered two-tile kernel attn_fwd2_kernel
+  //   'p<k>'     FMA-pipe exp2 for k of every 8 pairs
+  //   'f'        fwd2 only: the <4 tiles x 64 keys> shape (measured slower, see below);  'n'  fwd2 only: no exp-phase token
   const char* e = getenv("E4T_ATTN_FWD2");
-  int poly8 = 0, wide = 1, token = 1, dbuf = 0;
+  int poly8 = 0, wide = 1, token = 1, dbuf = 1;
   if (e) {
     if (e[0] == '0' && e[1] == 0) return 0;
     for (const char* c = e; *c; ++c) {
@@ -732,6 +758,7 @@ int e4t_attn_fwd2_try(const void* Q, const void* K, const void* V, void* O, floa
       if (*c == 'f') wide = 0;
       if (*c == 'n') token = 0;
       if (*c == 'd') dbuf = 1;
+      if (*c == 's') dbuf = 0;
     }
   }
   if (dh > 128 || M < 128 || N < 128) return 0;
@@ -751,13 +778,22 @@ int e4t_attn_fwd2_try(const void* Q, const void* K, const void* V, void* O, floa
     if (e4t_attn_make_head_map(&mQ, Q, dh, H, N, B, ldq, q_bs, 128)) return -1;
     if (e4t_attn_make_head_map(&mK, K, dh, H, M, B, ldk, k_bs, 96)) return -1;
     if (e4t_attn_make_head_map(&mV, V, dh, H, M, B, ldv, v_bs, 96)) return -1;
+    const dim3 grid3(cdiv(N, 256), H, B);
     static bool attr3 = false;
     if (!attr3) {
-      if (cudaFuncSetAttribute(attn_fwd3_kernel<96>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+      if (cudaFuncSetAttribute(attn_fwd3_kernel<96, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+          cudaFuncSetAttribute(attn_fwd3_kernel<96, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+          cudaFuncSetAttribute(attn_fwd3_kernel<96, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+          cudaFuncSetAttribute(attn_fwd3_kernel<96, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
         return -1;
       attr3 = true;
     }
-    attn_fwd3_kernel<96><<<dim3(cdiv(N, 256), H, B), 384, smem, st>>>(mQ, mK, mV, a);
+    switch (poly8) {
+      case 1: attn_fwd3_kernel<96, 1><<<grid3, 384, smem, st>>>(mQ, mK, mV, a); break;
+      case 2: attn_fwd3_kernel<96, 2><<<grid3, 384, smem, st>>>(mQ, mK, mV, a); break;
+      case 3: attn_fwd3_kernel<96, 3><<<grid3, 384, smem, st>>>(mQ, mK, mV, a); break;
+      default: attn_fwd3_kernel<96, 0><<<grid3, 384, smem, st>>>(mQ, mK, mV, a); break;
+    }
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
   }
   AttnArgs a;

@@ -14,7 +14,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 SWITCHES = ("E4T_ATTN_DQ_TMA", "E4T_ATTN_DELTA2", "E4T_ATTN_PT_TMEM", "E4T_ATTN_FWD_PT", "E4T_GEMM_EPI_PLAIN",
-            "E4T_ATTN_CG", "E4T_ATTN_FWD2")
+            "E4T_ATTN_CG", "E4T_ATTN_FWD2", "E4T_ATTN_BWD_REORD")
 
 
 @pytest.fixture(autouse=True)
@@ -36,6 +36,7 @@ def _rel(a, b):
 
 
 @pytest.mark.parametrize("env", [{"E4T_ATTN_DQ_TMA": "0"}, {"E4T_ATTN_DELTA2": "0"}, {"E4T_ATTN_PT_TMEM": "0"},
+                                 {"E4T_ATTN_BWD_REORD": "0"},
                                  {"E4T_ATTN_PT_TMEM": "0", "E4T_ATTN_DQ_TMA": "0", "E4T_ATTN_DELTA2": "0"}])
 @pytest.mark.parametrize("B,H,N,M,dh", [(2, 8, 256, 256, 40), (2, 8, 1024, 77, 40), (1, 8, 300, 200, 40),
                                         (1, 4, 384, 128, 64), (1, 8, 1024, 1024, 80), (1, 8, 4096, 4096, 40)])
@@ -62,12 +63,14 @@ def _attn_ref(q, k, v, H):
     return (s.softmax(-1) @ vh).transpose(1, 2).reshape(B, N, C), torch.logsumexp(s, -1)
 
 
-@pytest.mark.parametrize("fwd2", ["0", "p0", "np0", "fp0", "p2", "d"])
+@pytest.mark.parametrize("fwd2", ["0", "d", "dp2", "dp3", "s", "sn", "sf", "sp2"])
 @pytest.mark.parametrize("B,H,N,M,dh", [(2, 8, 256, 256, 40), (1, 8, 300, 200, 80), (2, 16, 257, 257, 80),
                                         (1, 8, 1024, 1024, 80), (2, 4, 384, 1000, 64), (1, 4, 256, 128, 128),
                                         (1, 8, 4096, 4096, 40)])
 def test_attention_forward_variants_vs_fp32_reference(fwd2, B, H, N, M, dh):
-    """Two-tile forward (all exp2 pipe splits) and the single-tile kernel against an fp32 torch softmax(QK^T)V.
+    """Forward variants against an fp32 torch softmax(QK^T)V: "0" the single-tile kernel, "d" the double-buffered-S kernel
+    (the default where it applies: dh <= 64, M >= 192) with its exp2 pipe splits, "s" the single-buffered two-tile kernel
+    (default elsewhere) with / without the exp-phase token, in its 4 x 64 shape and with a polynomial share.
     A strongly peaked row (scores spread over > 2^8 in the exp2 domain) exercises the threshold rescale, and the
     polynomial exp2 is exercised far below its clamp."""
     from e4t_b200 import ops

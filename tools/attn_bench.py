@@ -56,7 +56,7 @@ def main():
         if "fwd" in which:
             os.environ["E4T_ATTN_FWD2"] = "0"
             o_ref, lse_ref = ops.attn_fwd(*sets[0], H)
-            for tag in ("0", "p0", "d"):
+            for tag in ("0", "s", "d", "dp1", "dp2", "dp3"):
                 os.environ["E4T_ATTN_FWD2"] = tag
                 o, lse = ops.attn_fwd(*sets[0], H)
                 torch.cuda.synchronize()

@@ -19,7 +19,7 @@ def main():
         C = H * dh
         q, k, v = ((torch.randn(B, n, C, device="cuda") * 0.5).to(torch.bfloat16) for n in (N, M, M))
         q = q * peak
-        os.environ["E4T_ATTN_FWD2"] = "p0"
+        os.environ["E4T_ATTN_FWD2"] = "s"
         o0, l0 = ops.attn_fwd(q, k, v, H)
         os.environ["E4T_ATTN_FWD2"] = "d"
         o1, l1 = ops.attn_fwd(q, k, v, H)
