@@ -747,10 +747,11 @@ int e4t_attn_fwd2_try(const void* Q, const void* K, const void* V, void* O, floa
   // E4T_ATTN_FWD2: "0" disables these kernels (single-tile attn_fwd_kernel); otherwise a string of flags:
   //   'd' / 's'  force the double-buffered-S kernel attn_fwd3_kernel (default where it applies: dh <= 64, M >= 192) /
   //              the single-buffered two-tile kernel attn_fwd2_kernel
-  //   'p<k>'     FMA-pipe exp2 for k of every 8 pairs
+  //   'p<k>'     FMA-pipe exp2 for k of every 8 pairs (default: 2 in attn_fwd3_kernel — 0.701 vs 0.723 ms at level 0, r02
+  //              call 15 — and 0 in attn_fwd2_kernel, which waits for S rather than for the MUFU pipe)
   //   'f'        fwd2 only: the <4 tiles x 64 keys> shape (measured slower, see below);  'n'  fwd2 only: no exp-phase token
   const char* e = getenv("E4T_ATTN_FWD2");
-  int poly8 = 0, wide = 1, token = 1, dbuf = 1;
+  int poly8 = -1, wide = 1, token = 1, dbuf = 1;
   if (e) {
     if (e[0] == '0' && e[1] == 0) return 0;
     for (const char* c = e; *c; ++c) {
@@ -788,7 +789,7 @@ int e4t_attn_fwd2_try(const void* Q, const void* K, const void* V, void* O, floa
         return -1;
       attr3 = true;
     }
-    switch (poly8) {
+    switch (poly8 < 0 ? 2 : poly8) {
       case 1: attn_fwd3_kernel<96, 1><<<grid3, 384, smem, st>>>(mQ, mK, mV, a); break;
       case 2: attn_fwd3_kernel<96, 2><<<grid3, 384, smem, st>>>(mQ, mK, mV, a); break;
       case 3: attn_fwd3_kernel<96, 3><<<grid3, 384, smem, st>>>(mQ, mK, mV, a); break;

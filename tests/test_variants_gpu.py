@@ -63,7 +63,7 @@ def _attn_ref(q, k, v, H):
     return (s.softmax(-1) @ vh).transpose(1, 2).reshape(B, N, C), torch.logsumexp(s, -1)
 
 
-@pytest.mark.parametrize("fwd2", ["0", "d", "dp2", "dp3", "s", "sn", "sf", "sp2"])
+@pytest.mark.parametrize("fwd2", ["0", "d", "dp0", "dp3", "s", "sn", "sf", "sp2"])
 @pytest.mark.parametrize("B,H,N,M,dh", [(2, 8, 256, 256, 40), (1, 8, 300, 200, 80), (2, 16, 257, 257, 80),
                                         (1, 8, 1024, 1024, 80), (2, 4, 384, 1000, 64), (1, 4, 256, 128, 128),
                                         (1, 8, 4096, 4096, 40)])
