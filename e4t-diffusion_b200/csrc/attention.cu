@@ -1346,7 +1346,10 @@ extern "C" int e4t_attn_fwd(const void* Q, const void* K, const void* V, void* O
   a.BKV = M >= 128 ? 128 : round16(M);
   a.nblk = cdiv(M, a.BKV);
   // dh <= 64 and a long key axis: two CTAs per SM (256 TMEM columns, single S buffer, single K/V stage)
-  const bool occ2 = (a.DC == 1 && a.nblk >= 4 && attn_cg(3) != 0);
+  // ... or a single key block (cross-attention, M <= 128; E4T_ATTN_CG 4th field >= 2): nothing to pipeline inside the CTA, so a
+  // second resident CTA hides the fixed per-CTA latencies (TMEM alloc, barrier init, the one TMA -> MMA -> softmax -> MMA chain)
+  const int occ_mode = attn_cg(3);
+  const bool occ2 = a.DC == 1 && occ_mode != 0 && (a.nblk >= 4 || (occ_mode >= 2 && a.nblk == 1));
   a.kst = (a.DC >= 3 || occ2) ? 1 : 2;
   a.sbuf = occ2 ? 1 : 2;
   a.tmem_cols = occ2 ? 256 : 512;
