@@ -1300,7 +1300,8 @@ static int round16(int x) { return (x + 15) / 16 * 16; }
 static int attn_cg(int which) {
   // defaults 4,4,4 and two-CTAs-per-SM variants allowed; the environment is parsed on every call (cheap) so a tuning
   // script can sweep the variants in one process
-  int cfg[4] = {4, 4, 4, 1};
+  int cfg[4] = {4, 4, 4, 2};   // 4th: 0 never two CTAs/SM, 1 long key axes only, 2 also single-key-block shapes (0.132 -> 0.083 ms
+                               // at the level-0 cross-attention shape, r02 call 17)
   const char* e = getenv("E4T_ATTN_CG");
   if (e) sscanf(e, "%d,%d,%d,%d", &cfg[0], &cfg[1], &cfg[2], &cfg[3]);
   for (int i = 0; i < 3; ++i) if (cfg[i] != 2 && cfg[i] != 4) cfg[i] = 4;

@@ -100,6 +100,22 @@ def test_attention_forward_p_in_smem_matches_default(B, H, N, M, dh):
     assert _rel(o1, o0) < 1e-3, _rel(o1, o0)
 
 
+@pytest.mark.parametrize("B,H,N,M,dh", [(2, 8, 1024, 77, 40), (1, 8, 4096, 77, 40), (2, 4, 300, 128, 64)])
+def test_attention_forward_single_key_block_one_vs_two_ctas_per_sm(B, H, N, M, dh):
+    """Cross-attention shapes (one key block) run two CTAs per SM by default; the one-CTA launch must give the same result."""
+    from e4t_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(N + M + dh)
+    C = H * dh
+    q, k, v = _mk((B, N, C), g), _mk((B, M, C), g), _mk((B, M, C), g)
+    o0, lse0 = ops.attn_fwd(q, k, v, H)
+    oref, lse_ref = _attn_ref(q, k, v, H)
+    os.environ["E4T_ATTN_CG"] = "4,4,4,1"
+    o1, lse1 = ops.attn_fwd(q, k, v, H)
+    torch.cuda.synchronize()
+    assert _rel(o0, oref) < 6e-3 and (lse0 - lse_ref).abs().max().item() < 2e-2
+    assert _rel(o1, o0) < 2e-3 and (lse1 - lse0).abs().max().item() < 1e-4
+
+
 @pytest.mark.parametrize("M,N,K,b_mn", [(4096, 960, 320, False), (8192, 320, 320, False), (1000, 328, 192, False),
                                         (4096, 320, 960, True), (256, 64, 64, False)])
 def test_gemm_plain_epilogue_is_bit_identical(M, N, K, b_mn):

@@ -5,6 +5,7 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o launch_gap launch_gap.cu
 #include <cuda_runtime.h>
 #include <stdio.h>
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("%s:%d %s -> %s\n", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); return -1.f; } } while (0)
 
 template <int PDL>
 __global__ void __launch_bounds__(384, 1) k(long long work, int* sink, int smem_touch) {
@@ -20,10 +21,10 @@ __global__ void __launch_bounds__(384, 1) k(long long work, int* sink, int smem_
 
 static float run(int pdl, int n, long long work, size_t smem, int* sink) {
   cudaStream_t s;
-  cudaStreamCreate(&s);
+  CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
   cudaGraph_t g;
   cudaGraphExec_t ge;
-  cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
+  CK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
   for (int i = 0; i < n; ++i) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(148);
@@ -34,21 +35,22 @@ static float run(int pdl, int n, long long work, size_t smem, int* sink) {
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = pdl ? 1 : 0;
-    cudaError_t e = pdl ? cudaLaunchKernelEx(&cfg, k<1>, work, sink, 1) : cudaLaunchKernelEx(&cfg, k<0>, work, sink, 1);
-    if (e != cudaSuccess) { printf("launch error %s\n", cudaGetErrorString(e)); return -1.f; }
+    cfg.numAttrs = (pdl && i > 0) ? 1 : 0;     // the first node has no kernel predecessor
+    const int touch = 1;
+    if (pdl) CK(cudaLaunchKernelEx(&cfg, k<1>, work, sink, touch));
+    else CK(cudaLaunchKernelEx(&cfg, k<0>, work, sink, touch));
   }
-  if (cudaStreamEndCapture(s, &g) != cudaSuccess) { printf("capture failed\n"); return -1.f; }
-  if (cudaGraphInstantiate(&ge, g, 0) != cudaSuccess) { printf("instantiate failed\n"); return -1.f; }
+  CK(cudaStreamEndCapture(s, &g));
+  CK(cudaGraphInstantiate(&ge, g, 0));
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
-  cudaGraphLaunch(ge, s);
-  cudaStreamSynchronize(s);
+  CK(cudaGraphLaunch(ge, s));
+  CK(cudaStreamSynchronize(s));
   cudaEventRecord(e0, s);
   for (int r = 0; r < 5; ++r) cudaGraphLaunch(ge, s);
   cudaEventRecord(e1, s);
-  cudaStreamSynchronize(s);
+  CK(cudaStreamSynchronize(s));
   float ms = 0;
   cudaEventElapsedTime(&ms, e0, e1);
   cudaGraphExecDestroy(ge);
@@ -59,9 +61,12 @@ static float run(int pdl, int n, long long work, size_t smem, int* sink) {
 
 int main() {
   int* sink;
-  cudaMalloc(&sink, 4);
-  cudaFuncSetAttribute(k<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-  cudaFuncSetAttribute(k<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (cudaMalloc(&sink, 4) != cudaSuccess) return 1;
+  if (cudaFuncSetAttribute(k<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+      cudaFuncSetAttribute(k<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
+    printf("cudaFuncSetAttribute failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+    return 1;
+  }
   const int n = 1000;
   for (size_t smem : {(size_t)0, (size_t)200 * 1024}) {
     for (long long work : {0LL, 20000LL, 100000LL}) {   // 0, ~10 us, ~50 us of work per kernel
