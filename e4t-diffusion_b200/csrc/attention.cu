@@ -938,7 +938,8 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
   uint64_t* dq_empty = bars + 9;
   uint64_t* dq_staged = bars + 10;  // [2] DQTMA: every thread's part of the staging tile is in shared memory
   uint64_t* dq_free = bars + 12;    // [2] DQTMA: the TMA reduce has read the staging tile
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* pt_free = bars + 14;    // reordered issue: dV(j), the reader of P^T(j) in TMEM, has retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
@@ -955,6 +956,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
     mbar_init(acc_done, 1);
     mbar_init(dq_full, 1);
     mbar_init(dq_empty, 128 * CG);
+    mbar_init(pt_free, 1);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -1048,18 +1050,19 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
         }
         mbar_wait(ds_ready, (uint32_t)(j & 1));
         tc_fence_after();
+        if (reord && j + 1 < a.nblk) {           // S^T / dP^T of block j+1 first: the threads can start it ~650 clk from now
+          const int stn = st ^ 1;
+          mbar_wait(&q_full[stn], stn == 0 ? (ph ^ 1u) : ph);   // block j+1: next stage; the phase flips when it wraps to 0
+          tc_fence_after();
+          issue_s_dp((uint64_t)((uint32_t)stn * q_units));
+        }
 #pragma unroll
         for (int ks = 0; ks < BQ / 16; ++ks) {   // dV += P^T dO: A = P^T[:, 16 ks .. 16 ks + 16)
           const uint32_t acc = (j > 0 || ks > 0) ? 1u : 0u;
           if constexpr (PT) umma_bf16_ts(tdV, tPT + (uint32_t)(ks * 8), ddO_mn0 + so + (uint64_t)(ks * 128), idesc_o, acc);
           else umma_bf16(tdV, dPT_k + (uint64_t)(((ks >> 2) << 10) + ((ks & 3) << 1)), ddO_mn0 + so + (uint64_t)(ks * 128), idesc_o, acc);
         }
-        if (reord && j + 1 < a.nblk) {
-          const int stn = st ^ 1;
-          mbar_wait(&q_full[stn], stn == 0 ? (ph ^ 1u) : ph);   // block j+1: next stage; the phase flips when it wraps to 0
-          tc_fence_after();
-          issue_s_dp((uint64_t)((uint32_t)stn * q_units));
-        }
+        if (reord) umma_commit(pt_free);         // the threads of block j+1 may now overwrite P^T
 #pragma unroll
         for (int ks = 0; ks < BQ / 16; ++ks)     // dK += dS^T Q
           umma_bf16(tdK, dSk + (uint64_t)(((ks >> 2) << 10) + ((ks & 3) << 1)), dQ_mn0 + so + (uint64_t)(ks * 128),
@@ -1209,6 +1212,10 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
         uint8_t* pd = ((PT && a.kst == 2 && a.sbuf && (j & 1)) ? sPT : sdST) + (c >> 6) * 16384 + rowoff;
         const uint32_t cb = (uint32_t)((c & 63) >> 3);
         if constexpr (PT) {
+          if (a.kst == 2 && a.sbuf && j > 0 && c16 == cg) {   // reordered issue: dV(j-1) still reads P^T(j-1) after S/dP(j)
+            mbar_wait(pt_free, (uint32_t)((j - 1) & 1));
+            tc_fence_after();
+          }
           __syncwarp();
           tmem_st8(tPT + lane_base + (uint32_t)(c >> 1), wp);   // 16 bf16 of this key row -> 8 columns
         } else {
