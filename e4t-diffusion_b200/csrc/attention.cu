@@ -1050,12 +1050,14 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
         }
         mbar_wait(ds_ready, (uint32_t)(j & 1));
         tc_fence_after();
-        if (reord && j + 1 < a.nblk) {           // S^T / dP^T of block j+1 first: the threads can start it ~650 clk from now
+        auto next_s_dp = [&]() {
           const int stn = st ^ 1;
           mbar_wait(&q_full[stn], stn == 0 ? (ph ^ 1u) : ph);   // block j+1: next stage; the phase flips when it wraps to 0
           tc_fence_after();
           issue_s_dp((uint64_t)((uint32_t)stn * q_units));
-        }
+        };
+        // a.sbuf == 2: S^T / dP^T of block j+1 even before dV(j) (the threads then wait on pt_free before overwriting P^T)
+        if (reord && a.sbuf == 2 && j + 1 < a.nblk) next_s_dp();
 #pragma unroll
         for (int ks = 0; ks < BQ / 16; ++ks) {   // dV += P^T dO: A = P^T[:, 16 ks .. 16 ks + 16)
           const uint32_t acc = (j > 0 || ks > 0) ? 1u : 0u;
@@ -1063,10 +1065,12 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
           else umma_bf16(tdV, dPT_k + (uint64_t)(((ks >> 2) << 10) + ((ks & 3) << 1)), ddO_mn0 + so + (uint64_t)(ks * 128), idesc_o, acc);
         }
         if (reord) umma_commit(pt_free);         // the threads of block j+1 may now overwrite P^T
+        if (reord && a.sbuf != 2 && j + 1 < a.nblk) next_s_dp();
 #pragma unroll
         for (int ks = 0; ks < BQ / 16; ++ks)     // dK += dS^T Q
           umma_bf16(tdK, dSk + (uint64_t)(((ks >> 2) << 10) + ((ks & 3) << 1)), dQ_mn0 + so + (uint64_t)(ks * 128),
                     idesc_o, (j > 0 || ks > 0) ? 1u : 0u);
+        umma_commit(&q_empty[st]);               // dK was the last reader of this {Q, dO} stage (dQ reads dS^T and K only)
         if (j > 0) {
           mbar_wait(dq_empty, (uint32_t)((j - 1) & 1));  // threads have drained dQ_blk of block j-1
           tc_fence_after();
@@ -1074,7 +1078,6 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks)           // dQ_blk = dS K
           umma_bf16(tdQ, dSmn + (uint64_t)(ks * 128), dK_mn + (uint64_t)(ks * 128), idesc_q, ks > 0 ? 1u : 0u);
-        umma_commit(&q_empty[st]);
         umma_commit(dq_full);
         umma_commit(acc_done);
         if (++st == a.kst) {
@@ -1182,6 +1185,59 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
       asm volatile("bar.sync 1, %0;" ::"n"(NSOFT) : "memory");
       mbar_wait(sp_full, (uint32_t)(j & 1));
       tc_fence_after();
+      if constexpr (PT) {
+        // 8-column half chunks, software pipelined: the TMEM loads of half h+1 are in flight while half h is computed
+        // (one 16-column chunk at a time exposed a full tcgen05.ld latency per chunk; registers: 2 x {S, dP} x 8, as before).
+        // Half hh covers columns (cg + (hh >> 1) CG) 16 + (hh & 1) 8.
+        constexpr int NH = 2 * (BQ / 16) / CG;
+        uint8_t* pd_tile = ((a.kst == 2 && a.sbuf && (j & 1)) ? sPT : sdST) + rowoff;
+        uint32_t sA[8], dA[8], sB[8], dB[8];
+        __syncwarp();
+        tmem_ld8(tST + lane_base + (uint32_t)(cg * 16), sA);
+        tmem_ld8(tdPT + lane_base + (uint32_t)(cg * 16), dA);
+        tmem_ld_wait();
+#pragma unroll
+        for (int hh = 0; hh < NH; ++hh) {
+          const int c = (cg + (hh >> 1) * CG) * 16 + (hh & 1) * 8;
+          if (hh + 1 < NH) {
+            const int cn = (cg + ((hh + 1) >> 1) * CG) * 16 + ((hh + 1) & 1) * 8;
+            __syncwarp();
+            tmem_ld8(tST + lane_base + (uint32_t)cn, (hh & 1) ? sA : sB);
+            tmem_ld8(tdPT + lane_base + (uint32_t)cn, (hh & 1) ? dA : dB);
+          }
+          const uint32_t* sr = (hh & 1) ? sB : sA;
+          const uint32_t* dr = (hh & 1) ? dB : dA;
+          uint32_t wp[4], wd[4];
+#pragma unroll
+          for (int e = 0; e < 4; e += 2) {
+            const float4 ls = *reinterpret_cast<const float4*>(&sLSE[c + 2 * e]);
+            const float4 dd = *reinterpret_cast<const float4*>(&sD[c + 2 * e]);
+            const float p0 = ex2_approx(fmaf(__uint_as_float(sr[2 * e]), sl2, -ls.x));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(sr[2 * e + 1]), sl2, -ls.y));
+            const float p2 = ex2_approx(fmaf(__uint_as_float(sr[2 * e + 2]), sl2, -ls.z));
+            const float p3 = ex2_approx(fmaf(__uint_as_float(sr[2 * e + 3]), sl2, -ls.w));
+            wp[e] = pack_bf16(p0, p1);
+            wp[e + 1] = pack_bf16(p2, p3);
+            wd[e] = pack_bf16(p0 * fmaf(__uint_as_float(dr[2 * e]), a.scale, -dd.x),
+                              p1 * fmaf(__uint_as_float(dr[2 * e + 1]), a.scale, -dd.y));
+            wd[e + 1] = pack_bf16(p2 * fmaf(__uint_as_float(dr[2 * e + 2]), a.scale, -dd.z),
+                                  p3 * fmaf(__uint_as_float(dr[2 * e + 3]), a.scale, -dd.w));
+          }
+          if (!kv_ok) {   // keys past M (only in the last key tile): contribute nothing
+#pragma unroll
+            for (int e = 0; e < 4; ++e) wp[e] = wd[e] = 0u;
+          }
+          if (hh == 0 && a.kst == 2 && a.sbuf && j > 0) {   // reordered issue: dV(j-1) still reads P^T(j-1) after S/dP(j)
+            mbar_wait(pt_free, (uint32_t)((j - 1) & 1));
+            tc_fence_after();
+          }
+          __syncwarp();
+          tmem_st4(tPT + lane_base + (uint32_t)(c >> 1), wp);   // 8 bf16 of this key row -> 4 columns
+          const uint32_t cb = (uint32_t)((c & 63) >> 3);
+          *reinterpret_cast<uint4*>(pd_tile + (c >> 6) * 16384 + ((cb ^ r7) << 4)) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+          if (hh + 1 < NH) tmem_ld_wait();
+        }
+      } else {
       // 16-column chunks (two TMEM loads in flight per chunk); chunk c16 belongs to column group (c16 % CG)
       for (int c16 = cg; c16 < BQ / 16; c16 += CG) {
         const int c = c16 * 16;
@@ -1209,7 +1265,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
 #pragma unroll
           for (int e = 0; e < 8; ++e) wp[e] = wd[e] = 0u;
         }
-        uint8_t* pd = ((PT && a.kst == 2 && a.sbuf && (j & 1)) ? sPT : sdST) + (c >> 6) * 16384 + rowoff;
+        uint8_t* pd = sdST + (c >> 6) * 16384 + rowoff;
         const uint32_t cb = (uint32_t)((c & 63) >> 3);
         if constexpr (PT) {
           if (a.kst == 2 && a.sbuf && j > 0 && c16 == cg) {   // reordered issue: dV(j-1) still reads P^T(j-1) after S/dP(j)
@@ -1225,6 +1281,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
         }
         *reinterpret_cast<uint4*>(pd + ((cb ^ r7) << 4)) = make_uint4(wd[0], wd[1], wd[2], wd[3]);
         *reinterpret_cast<uint4*>(pd + (((cb + 1) ^ r7) << 4)) = make_uint4(wd[4], wd[5], wd[6], wd[7]);
+      }
       }
       if constexpr (PT) tmem_st_wait();
       fence_proxy_async_smem();
@@ -1538,7 +1595,7 @@ extern "C" int e4t_attn_bwd_fused(const void* Q, const void* K, const void* V, c
   const bool pt_tmem = (!pte || atoi(pte) != 0) && 256 + 3 * dpad + 64 <= 512;   // default ON
   {   // (field reused) 1 = reordered MMA issue with double-buffered dS^T (default; E4T_ATTN_BWD_REORD=0 keeps the block order)
     const char* re = getenv("E4T_ATTN_BWD_REORD");
-    a.sbuf = (!re || atoi(re) != 0) ? 1 : 0;
+    a.sbuf = re ? atoi(re) : 1;       // 0 block order, 1 dV(j) | S,dP(j+1) | dK,dQ(j), 2 S,dP(j+1) | dV(j) | dK,dQ(j)
   }
   CUtensorMap mDQ;
   memset(&mDQ, 0, sizeof(mDQ));

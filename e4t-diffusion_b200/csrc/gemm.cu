@@ -460,7 +460,7 @@ static int num_sms() {
 // Choosing BN with this model costs 39.1 ms/step over the 116 signatures, against 38.8 ms for the per-signature best and
 // 44.4 ms for the round-1 model (max(2*BN, 128+BN) per chunk), which preferred tiles that were too narrow.
 static int pick_bn(int N, long m_tiles_x_batch, bool b_mn, int force_bn, int kchunks_per_tile = 16,
-                   bool residual = false, bool atomic = false) {
+                   bool residual = false, bool atomic = false, double* cost_out = nullptr) {
   if (force_bn > 0) return force_bn;
   const int step = b_mn ? 64 : 32;
   int best = 0;
@@ -477,6 +477,28 @@ static int pick_bn(int N, long m_tiles_x_batch, bool b_mn, int force_bn, int kch
     if (cost < best_cost - 1e-6) {
       best_cost = cost;
       best = bn;
+    }
+  }
+  if (cost_out) *cost_out = best_cost;
+  return best;
+}
+
+// Split-K factor of an fp32-accumulating GEMM (weight gradients: small M x N, very long K) by the same cost model: the
+// factor that minimises rounds x max(mainloop, atomic epilogue) + epilogue.  (Round 2: "fill the machine about twice"
+// from 128 x 128 tile counts gave e.g. 13 splits x 16 tiles = 208 CTAs for the level-0 QKV weight gradient — 1.4 rounds of
+// the 148-CTA persistent grid; 9 splits = 144 CTAs do the same work in one.)
+static int auto_splits(int N, long m_tiles_x_batch, bool b_mn, int kchunks) {
+  int best = 1;
+  double best_cost = 1e30;
+  const int smax = kchunks < 64 ? kchunks : 64;
+  for (int sp = 1; sp <= smax; ++sp) {
+    const int kper = cdiv(kchunks, sp);
+    if (cdiv(kchunks, kper) != sp) continue;          // same kper as a smaller factor
+    double c = 0;
+    pick_bn(N, m_tiles_x_batch * sp, b_mn, 0, kper, false, true, &c);
+    if (c < best_cost - 1e-6) {
+      best_cost = c;
+      best = sp;
     }
   }
   return best;
@@ -543,6 +565,7 @@ extern "C" int e4t_gemm_bf16(const void* A, const void* B, void* out, int M, int
   g.a_batched = (a_bstride != 0); g.b_batched = (b_bstride != 0);
   g.m_tiles = cdiv(M, kBM);
   g.kchunks = cdiv(K, kBK);
+  if (splits == 0 && out_mode == 2 && force_bn <= 0) splits = auto_splits(N, (long)g.m_tiles * batch, b_mn != 0, g.kchunks);
   if (splits < 1) splits = 1;
   if (splits > g.kchunks) splits = g.kchunks;
   g.kper = cdiv(g.kchunks, splits);

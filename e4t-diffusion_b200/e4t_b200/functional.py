@@ -72,8 +72,8 @@ def as_bf16(t):
 # dense layers
 # ----------------------------------------------------------------------------------------------
 def _wgrad_splits(m, C, R):
-    tiles = ((C + 127) // 128) * ((R + 127) // 128)
-    return max(1, min((m + 63) // 64, (2 * 148 + tiles - 1) // tiles))
+    """Split-K factor of a weight-gradient GEMM: 0 = chosen inside the library by its tile cost model (gemm.cu auto_splits)."""
+    return 0
 
 
 class LinearFn(torch.autograd.Function):
@@ -164,9 +164,7 @@ class WOLinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[2]:
             m = x2.shape[0]
             dw = torch.zeros((C, R), device=x2.device, dtype=F32)
-            tiles = ((C + 127) // 128) * ((R + 127) // 128)
-            splits = max(1, min((m + 63) // 64, (2 * 148 + tiles - 1) // tiles))
-            ops.gemm(dy2, x2, a_mn=True, b_mn=True, out=dw, accumulate=True, splits=splits)
+            ops.gemm(dy2, x2, a_mn=True, b_mn=True, out=dw, accumulate=True, splits=_wgrad_splits(m, C, R))
         return dx, None, dw
 
 
@@ -191,9 +189,7 @@ class WOLinearBankFn(torch.autograd.Function):
         dy2 = _c(dy).view(-1, C)
         dx = ops.gemm(dy2, w_eff, b_mn=True).view(ctx.shp) if ctx.needs_input_grad[0] else None
         m = x2.shape[0]
-        tiles = ((C + 127) // 128) * ((R + 127) // 128)
-        splits = max(1, min((m + 63) // 64, (2 * 148 + tiles - 1) // tiles))
-        ops.gemm(dy2, x2, a_mn=True, b_mn=True, out=ctx.dweff, accumulate=True, splits=splits)
+        ops.gemm(dy2, x2, a_mn=True, b_mn=True, out=ctx.dweff, accumulate=True, splits=_wgrad_splits(m, C, R))
         return dx, None, None, None
 
 

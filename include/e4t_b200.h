@@ -28,6 +28,7 @@ void e4t_reset_launch_count(void);
  * a_mn / b_mn = 0: operand stored [rows][K] (K contiguous); = 1: stored [K][rows] (rows contiguous).
  * lda/ldb: row stride in elements (multiple of 8); a_bstride/b_bstride: batch stride, 0 = shared across the batch.
  * out_mode 0: bf16 store, 1: fp32 store, 2: fp32 atomic accumulate (required when splits > 1: split-K).
+ * splits: split-K factor; 0 with out_mode 2 = chosen by the library's tile cost model (weight gradients).
  * force_bn: N-tile override for tuning (0 = heuristic). */
 int e4t_gemm_bf16(const void* A, const void* B, void* out, int M, int N, int K, int batch, int a_mn, int b_mn,
                   long long lda, long long ldb, long long a_bstride, long long b_bstride, int out_mode,

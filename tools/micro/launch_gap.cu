@@ -68,7 +68,7 @@ int main() {
     return 1;
   }
   const int n = 1000;
-  for (size_t smem : {(size_t)0, (size_t)200 * 1024}) {
+  for (size_t smem : {(size_t)2048, (size_t)200 * 1024}) {
     for (long long work : {0LL, 20000LL, 100000LL}) {   // 0, ~10 us, ~50 us of work per kernel
       const float a = run(0, n, work, smem, sink), b = run(1, n, work, smem, sink);
       printf("smem %3zu KiB  work %6lld clk (%5.1f us): plain %6.2f us/launch   PDL %6.2f us/launch\n", smem >> 10, work,
