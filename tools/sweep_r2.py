@@ -179,7 +179,7 @@ def sweep_gemm():
     totb = sum(r["step_ms_best"] or 0 for r in rows)
     print(f"[gemm] {len(rows)} signatures, sum(calls x default) = {tot:.2f} ms/step, with best forced BN {totb:.2f} ms "
           f"({time.time()-t0:.0f}s)")
-    for r in rows[:25]:
+    for r in rows[:70]:
         print(f"  {r['calls']:3d} x {r['ms_default']*1e3 if r['ms_default'] else 0:7.1f} us = {r['step_ms_default'] or 0:6.2f} ms  "
               f"{r['tflops_default'] or 0:6.0f} TF/s  best bn {r['best_bn']} {((r['ms_best'] or 0)*1e3):7.1f} us  "
               f"plain-epi {r['ms_plain_epilogue']} eq={r['plain_equal']}  {r['sig']}")
