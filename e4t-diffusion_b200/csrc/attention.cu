@@ -908,7 +908,7 @@ __device__ __forceinline__ void mma_ds_k(uint32_t d_tmem, uint32_t sdST, uint32_
 // PT (opt-in, E4T_ATTN_PT_TMEM=1): the threads write Pᵀ into 64 TMEM columns (tcgen05.st) and dV += Pᵀ·dO takes its A
 // operand from TMEM: no Pᵀ stores to shared memory and no 4 KiB A-tile read per N=48 MMA (which is what makes those
 // MMAs shared-memory-bandwidth bound: 5.5 KiB of operands per 24-clk instruction against 128 B/clk).
-template <int CG, bool DQTMA, bool PT>
+template <int CG, bool DQTMA, bool PT, bool CAUSAL = false>
 __global__ void __launch_bounds__(128 + 128 * CG, 1)
 attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                       const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapdO,
@@ -1212,10 +1212,17 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
           for (int e = 0; e < 4; e += 2) {
             const float4 ls = *reinterpret_cast<const float4*>(&sLSE[c + 2 * e]);
             const float4 dd = *reinterpret_cast<const float4*>(&sD[c + 2 * e]);
-            const float p0 = ex2_approx(fmaf(__uint_as_float(sr[2 * e]), sl2, -ls.x));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(sr[2 * e + 1]), sl2, -ls.y));
-            const float p2 = ex2_approx(fmaf(__uint_as_float(sr[2 * e + 2]), sl2, -ls.z));
-            const float p3 = ex2_approx(fmaf(__uint_as_float(sr[2 * e + 3]), sl2, -ls.w));
+            float p0 = ex2_approx(fmaf(__uint_as_float(sr[2 * e]), sl2, -ls.x));
+            float p1 = ex2_approx(fmaf(__uint_as_float(sr[2 * e + 1]), sl2, -ls.y));
+            float p2 = ex2_approx(fmaf(__uint_as_float(sr[2 * e + 2]), sl2, -ls.z));
+            float p3 = ex2_approx(fmaf(__uint_as_float(sr[2 * e + 3]), sl2, -ls.w));
+            if constexpr (CAUSAL) {   // key kv attends only to queries >= kv: P and dS of earlier queries are exactly 0
+              const int qb = j * BQ + c + 2 * e;
+              p0 = kv > qb ? 0.f : p0;
+              p1 = kv > qb + 1 ? 0.f : p1;
+              p2 = kv > qb + 2 ? 0.f : p2;
+              p3 = kv > qb + 3 ? 0.f : p3;
+            }
             wp[e] = pack_bf16(p0, p1);
             wp[e + 1] = pack_bf16(p2, p3);
             wd[e] = pack_bf16(p0 * fmaf(__uint_as_float(dr[2 * e]), a.scale, -dd.x),
@@ -1250,10 +1257,17 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_con
         for (int e = 0; e < 8; e += 2) {
           const float4 ls = *reinterpret_cast<const float4*>(&sLSE[c + 2 * e]);
           const float4 dd = *reinterpret_cast<const float4*>(&sD[c + 2 * e]);
-          const float p0 = ex2_approx(fmaf(__uint_as_float(sreg[2 * e]), sl2, -ls.x));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(sreg[2 * e + 1]), sl2, -ls.y));
-          const float p2 = ex2_approx(fmaf(__uint_as_float(sreg[2 * e + 2]), sl2, -ls.z));
-          const float p3 = ex2_approx(fmaf(__uint_as_float(sreg[2 * e + 3]), sl2, -ls.w));
+          float p0 = ex2_approx(fmaf(__uint_as_float(sreg[2 * e]), sl2, -ls.x));
+          float p1 = ex2_approx(fmaf(__uint_as_float(sreg[2 * e + 1]), sl2, -ls.y));
+          float p2 = ex2_approx(fmaf(__uint_as_float(sreg[2 * e + 2]), sl2, -ls.z));
+          float p3 = ex2_approx(fmaf(__uint_as_float(sreg[2 * e + 3]), sl2, -ls.w));
+          if constexpr (CAUSAL) {
+            const int qb = j * BQ + c + 2 * e;
+            p0 = kv > qb ? 0.f : p0;
+            p1 = kv > qb + 1 ? 0.f : p1;
+            p2 = kv > qb + 2 ? 0.f : p2;
+            p3 = kv > qb + 3 ? 0.f : p3;
+          }
           wp[e] = pack_bf16(p0, p1);
           wp[e + 1] = pack_bf16(p2, p3);
           wd[e] = pack_bf16(p0 * fmaf(__uint_as_float(dp[2 * e]), a.scale, -dd.x),
@@ -1538,18 +1552,17 @@ extern "C" int e4t_attn_bwd(const void* Q, const void* K, const void* V, const v
   return 0;
 }
 
-// Fused backward (one pass over the (query block, key tile) pairs).  dQacc: fp32 scratch [B][N][H*dh] (zeroed here).
-// Falls back to the two-kernel path when the head dim does not fit the TMEM budget (dh > 80) or N is tiny.
-extern "C" int e4t_attn_bwd_fused(const void* Q, const void* K, const void* V, const void* O, const void* dO,
-                                  const float* LSE, float* Dv, float* dQacc, void* dQ, void* dK, void* dV, int B, int H,
-                                  int N, int M, int dh, long long ldq, long long q_bs, long long ldk, long long k_bs,
-                                  long long ldv, long long v_bs, long long ldo, long long o_bs, long long lddo,
-                                  long long do_bs, long long lddq, long long dq_bs, long long lddk, long long dk_bs,
-                                  long long lddv, long long dv_bs, float scale, void* stream_) {
+static int attn_bwd_fused_impl(const void* Q, const void* K, const void* V, const void* O, const void* dO,
+                               const float* LSE, float* Dv, float* dQacc, void* dQ, void* dK, void* dV, int B, int H,
+                               int N, int M, int dh, long long ldq, long long q_bs, long long ldk, long long k_bs,
+                               long long ldv, long long v_bs, long long ldo, long long o_bs, long long lddo,
+                               long long do_bs, long long lddq, long long dq_bs, long long lddk, long long dk_bs,
+                               long long lddv, long long dv_bs, float scale, int causal, void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   if (int e = attn_common_checks(dh, ldq, ldk, ldv)) return e;
   const int dpad = round16(dh);
-  if (256 + 3 * dpad > 512 || N < 128)
+  E4T_CHECK(!causal || (256 + 3 * dpad <= 512 && N == M), "e4t_attn_bwd_fused_causal: needs dh <= 80 and N == M");
+  if (!causal && (256 + 3 * dpad > 512 || N < 128))
     return e4t_attn_bwd(Q, K, V, O, dO, LSE, Dv, dQ, dK, dV, B, H, N, M, dh, ldq, q_bs, ldk, k_bs, ldv, v_bs, ldo, o_bs,
                         lddo, do_bs, lddq, dq_bs, lddk, dk_bs, lddv, dv_bs, scale, stream_);
   E4T_CHECK(lddo % 8 == 0 && lddq % 8 == 0 && lddk % 8 == 0 && lddv % 8 == 0, "e4t_attn_bwd_fused: strides %% 8");
@@ -1564,6 +1577,8 @@ extern "C" int e4t_attn_bwd_fused(const void* Q, const void* K, const void* V, c
     E4T_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel<4, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     E4T_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel<4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     E4T_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel<4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    E4T_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel<4, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    E4T_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel<4, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr = true;
   }
   AttnArgs a;
@@ -1605,7 +1620,14 @@ extern "C" int e4t_attn_bwd_fused(const void* Q, const void* K, const void* V, c
     const uint32_t box[3] = {(uint32_t)dh, 128, 1};
     if (int e = e4t_tmap_encode(&mDQ, dQacc, 3, dims, str, box, 4, 0)) return e;
   }
-  if (dq_tma && pt_tmem) {
+  a.causal = causal;
+  if (causal && dq_tma && pt_tmem) {
+    attn_bwd_fused_kernel<4, true, true, true><<<dim3(cdiv(M, 128), H, B), 128 + 128 * 4, smem + 2 * 128 * dh * 4, st>>>(
+        mQ, mK, mV, mdO, mDQ, a, dQacc);
+  } else if (causal) {
+    attn_bwd_fused_kernel<4, false, false, true><<<dim3(cdiv(M, 128), H, B), 128 + 128 * 4, smem, st>>>(mQ, mK, mV, mdO, mDQ,
+                                                                                                         a, dQacc);
+  } else if (dq_tma && pt_tmem) {
     attn_bwd_fused_kernel<4, true, true><<<dim3(cdiv(M, 128), H, B), 128 + 128 * 4, smem + 2 * 128 * dh * 4, st>>>(
         mQ, mK, mV, mdO, mDQ, a, dQacc);
   } else if (dq_tma) {
@@ -1625,4 +1647,28 @@ extern "C" int e4t_attn_bwd_fused(const void* Q, const void* K, const void* V, c
   E4T_COUNT_LAUNCH();
   E4T_LAUNCH_CHECK();
   return 0;
+}
+
+// Fused backward (one pass over the (query block, key tile) pairs).  dQacc: fp32 scratch [B][N][H*dh] (zeroed here).
+// Falls back to the two-kernel path when the head dim does not fit the TMEM budget (dh > 80) or N is tiny.
+extern "C" int e4t_attn_bwd_fused(const void* Q, const void* K, const void* V, const void* O, const void* dO,
+                                  const float* LSE, float* Dv, float* dQacc, void* dQ, void* dK, void* dV, int B, int H,
+                                  int N, int M, int dh, long long ldq, long long q_bs, long long ldk, long long k_bs,
+                                  long long ldv, long long v_bs, long long ldo, long long o_bs, long long lddo,
+                                  long long do_bs, long long lddq, long long dq_bs, long long lddk, long long dk_bs,
+                                  long long lddv, long long dv_bs, float scale, void* stream_) {
+  return attn_bwd_fused_impl(Q, K, V, O, dO, LSE, Dv, dQacc, dQ, dK, dV, B, H, N, M, dh, ldq, q_bs, ldk, k_bs, ldv, v_bs, ldo,
+                             o_bs, lddo, do_bs, lddq, dq_bs, lddk, dk_bs, lddv, dv_bs, scale, 0, stream_);
+}
+// The same with a causal mask (key j contributes to query i only if j <= i; N == M, dh <= 80, any N): the backward of the
+// CLIP text tower's self-attention (e4t/models/modeling_clip.py:45-51) on the tensor cores.  O and LSE come from the
+// forward that applied the same mask (e4t_attn_small_fwd).
+extern "C" int e4t_attn_bwd_fused_causal(const void* Q, const void* K, const void* V, const void* O, const void* dO,
+                                         const float* LSE, float* Dv, float* dQacc, void* dQ, void* dK, void* dV, int B,
+                                         int H, int N, int M, int dh, long long ldq, long long q_bs, long long ldk,
+                                         long long k_bs, long long ldv, long long v_bs, long long ldo, long long o_bs,
+                                         long long lddo, long long do_bs, long long lddq, long long dq_bs, long long lddk,
+                                         long long dk_bs, long long lddv, long long dv_bs, float scale, void* stream_) {
+  return attn_bwd_fused_impl(Q, K, V, O, dO, LSE, Dv, dQacc, dQ, dK, dV, B, H, N, M, dh, ldq, q_bs, ldk, k_bs, ldv, v_bs, ldo,
+                             o_bs, lddo, do_bs, lddq, dq_bs, lddk, dk_bs, lddv, dv_bs, scale, 1, stream_);
 }

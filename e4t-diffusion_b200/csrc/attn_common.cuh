@@ -14,6 +14,7 @@ struct AttnArgs {
   int sbuf;      // fwd: S accumulator buffers in TMEM (2 = software pipelined, 1 = rely on 2 CTAs/SM)
   int pbuf;      // fwd: P buffers in smem (2 = softmax never waits for the previous P·V to retire)
   int tmem_cols; // TMEM columns to allocate (256 lets two CTAs share an SM)
+  int causal;    // fused backward only: keys after the query are masked (CLIP text tower)
   float scale;   // dh^-0.5
   // pointers / strides (elements)
   bf16* O;  long long ldo, o_bs;

@@ -413,8 +413,14 @@ class SmallAttentionFn(torch.autograd.Function):
         C = qkv.shape[-1] // 3
         q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
         d = torch.empty_like(qkv)
-        ops.attn_small_bwd(q, k, v, o, _c(do), lse, heads, scale, causal, dq=d[..., :C], dk=d[..., C:2 * C],
-                           dv=d[..., 2 * C:])
+        if causal and q.shape[1] == k.shape[1] and (C // heads) % 8 == 0 and C // heads <= 80 and (3 * C) % 8 == 0:
+            # tensor-core fused backward with the causal mask (33 us against 129 us for the scalar kernel at the CLIP-L
+            # text shape 16 x 12 x 77 x 64, r02 call 21)
+            ops.attn_bwd(q, k, v, o, _c(do), lse, heads, scale, dq=d[..., :C], dk=d[..., C:2 * C], dv=d[..., 2 * C:],
+                         causal=True)
+        else:
+            ops.attn_small_bwd(q, k, v, o, _c(do), lse, heads, scale, causal, dq=d[..., :C], dk=d[..., C:2 * C],
+                               dv=d[..., 2 * C:])
         return d, None, None, None
 
 

@@ -311,10 +311,12 @@ def attn_fwd(q, k, v, heads, scale=None):
     return o, lse
 
 
-def attn_bwd(q, k, v, o, do, lse, heads, scale=None, dq=None, dk=None, dv=None, fused=True):
+def attn_bwd(q, k, v, o, do, lse, heads, scale=None, dq=None, dk=None, dv=None, fused=True, causal=False):
     """dq/dk/dv may be preallocated (e.g. column slices of one fused (B,N,3C) gradient buffer).
     fused=True: single-pass backward (S/dP computed once per tile pair, dQ reduced in fp32) when the head dim fits
-    the TMEM budget (dh <= 80); otherwise / fused=False the two-kernel (dQ, dK/dV) path."""
+    the TMEM budget (dh <= 80); otherwise / fused=False the two-kernel (dQ, dK/dV) path.
+    causal=True (N == M, dh <= 80): key j contributes to query i only if j <= i; o / lse must come from a forward that
+    applied the same mask (attn_small_fwd)."""
     assert do.dtype == BF16 and do.stride(-1) == 1
     Bn, N, C = q.shape
     M = k.shape[1]
@@ -325,9 +327,10 @@ def attn_bwd(q, k, v, o, do, lse, heads, scale=None, dq=None, dk=None, dv=None, 
     dv = torch.empty((Bn, M, C), device=q.device, dtype=BF16) if dv is None else dv
     assert dq.stride(-1) == 1 and dk.stride(-1) == 1 and dv.stride(-1) == 1
     dlt = torch.empty((Bn, heads, N), device=q.device, dtype=F32)
-    if fused and dh <= 80 and N >= 128:
+    assert not causal or (dh <= 80 and N == M), "causal attention backward: dh <= 80 and N == M"
+    if causal or (fused and dh <= 80 and N >= 128):
         dqacc = torch.empty((Bn, N, C), device=q.device, dtype=F32)
-        _lib.call("e4t_attn_bwd_fused", ptr(q), ptr(k), ptr(v), ptr(o), ptr(do), ptr(lse), ptr(dlt), ptr(dqacc),
+        _lib.call("e4t_attn_bwd_fused_causal" if causal else "e4t_attn_bwd_fused", ptr(q), ptr(k), ptr(v), ptr(o), ptr(do), ptr(lse), ptr(dlt), ptr(dqacc),
                   ptr(dq), ptr(dk), ptr(dv), c_int(Bn), c_int(heads), c_int(N), c_int(M), c_int(dh),
                   c_ll(q.stride(1)), c_ll(_bs(q)), c_ll(k.stride(1)), c_ll(_bs(k)), c_ll(v.stride(1)), c_ll(_bs(v)),
                   c_ll(o.stride(1)), c_ll(_bs(o)), c_ll(do.stride(1)), c_ll(_bs(do)), c_ll(dq.stride(1)),

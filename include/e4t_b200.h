@@ -78,6 +78,13 @@ int e4t_attn_bwd_fused(const void* Q, const void* K, const void* V, const void* 
                        long long ldq, long long q_bs, long long ldk, long long k_bs, long long ldv, long long v_bs,
                        long long ldo, long long o_bs, long long lddo, long long do_bs, long long lddq, long long dq_bs,
                        long long lddk, long long dk_bs, long long lddv, long long dv_bs, float scale, void* stream);
+/* The same with a causal mask (key j contributes to query i only if j <= i; N == M, dh <= 80, any N): backward of the CLIP
+ * text tower's masked self-attention, e4t/models/modeling_clip.py:45-51.  O / LSE from e4t_attn_small_fwd(causal = 1). */
+int e4t_attn_bwd_fused_causal(const void* Q, const void* K, const void* V, const void* O, const void* dO, const float* LSE,
+                       float* Dv, float* dQacc, void* dQ, void* dK, void* dV, int B, int H, int N, int M, int dh,
+                       long long ldq, long long q_bs, long long ldk, long long k_bs, long long ldv, long long v_bs,
+                       long long ldo, long long o_bs, long long lddo, long long do_bs, long long lddq, long long dq_bs,
+                       long long lddk, long long dk_bs, long long lddv, long long dv_bs, float scale, void* stream);
 
 /* Short-sequence attention (N, M <= 128, dh <= 64) with optional causal mask: the CLIP text tower's 77-token causal
  * self-attention (e4t/models/modeling_clip.py:45-51, HF CLIPAttention) and its backward.  Same layout as e4t_attn_fwd. */

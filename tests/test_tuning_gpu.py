@@ -132,6 +132,36 @@ def test_small_attention_fwd_bwd(B, H, N, dh, causal):
     assert _rel(got, o) < 6e-3 and _rel(qkv.grad, r.grad) < 1e-2
 
 
+@pytest.mark.parametrize("B,H,N,dh", [(16, 12, 77, 64), (2, 8, 128, 40), (1, 4, 200, 80), (3, 2, 5, 16)])
+def test_causal_attention_backward_tensor_core_vs_scalar_kernel(B, H, N, dh):
+    """The fused tcgen05 backward with the causal mask (what SmallAttentionFn.backward runs for the CLIP text tower)
+    against the scalar small-attention backward on the same (o, lse) — where the scalar kernel applies (N <= 128) — and
+    against fp32 torch."""
+    from e4t_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(N + dh)
+    C = H * dh
+    qkv = _mk((B, N, 3 * C), g)
+    q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+    do = _mk((B, N, C), g)
+    r = qkv.float().requires_grad_(True)
+    qr, kr, vr = (t.view(B, N, H, dh).transpose(1, 2) for t in r.chunk(3, dim=-1))
+    s = (qr @ kr.transpose(-1, -2)) * dh ** -0.5
+    s = s.masked_fill(torch.ones(N, N, device="cuda", dtype=torch.bool).triu(1), float("-inf"))
+    oref = (s.softmax(-1) @ vr).transpose(1, 2).reshape(B, N, C)
+    oref.backward(do.float())
+    lse = torch.logsumexp(s.detach(), -1).contiguous()
+    o = oref.detach().to(torch.bfloat16)
+    d = torch.empty_like(qkv)
+    ops.attn_bwd(q, k, v, o, do, lse, H, dq=d[..., :C], dk=d[..., C:2 * C], dv=d[..., 2 * C:], causal=True)
+    torch.cuda.synchronize()
+    assert _rel(d, r.grad) < 1e-2, _rel(d, r.grad)
+    if N <= 128 and dh <= 64:
+        d2 = torch.empty_like(qkv)
+        ops.attn_small_bwd(q, k, v, o, do, lse, H, None, True, dq=d2[..., :C], dk=d2[..., C:2 * C], dv=d2[..., 2 * C:])
+        torch.cuda.synchronize()
+        assert _rel(d, d2) < 6e-3, _rel(d, d2)
+
+
 @pytest.mark.parametrize("mode", [0, 1, 2])
 def test_activations(mode):
     from e4t_b200 import functional as FN
