@@ -539,7 +539,8 @@ def main():
                 traffic, traffic_src = tj["dram_bytes_read"] + tj["dram_bytes_write"], tj["source"]
         except Exception:
             pass
-        roof = {"kernel": "attention forward core (attn_fwd2_kernel; level-0 self-attention, N=M=4096, 8x40, B=%d)" % B,
+        roof = {"kernel": ("attention forward core (attn_fwd3_kernel: two S buffers per tile in TMEM, exp2 split 2/8 over MUFU/FMA; "
+                           "level-0 self-attention, N=M=4096, 8x40, B=%d)" % B),
                 "bound": "tensor", "achieved": a["tflops"], "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
                 "frac": a["tflops"] / peaks["bf16_burst"], "traffic": traffic, "traffic_source": traffic_src,
                 "algorithmic_flops_per_launch": a["flops"],
