@@ -234,10 +234,11 @@ e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       const bf16* res = (g.residual && row_ok) ? g.residual + (long long)bz * g.res_bstride + (long long)m * g.ldr
                                                : nullptr;
       if (g.debug & 1) {
-      } else if (g.tma_store && g.epi_plain && !g.bias && !g.rowgroup && !g.residual && g.alpha == 1.f) {
-        // ---- plain bf16 output (QKV projections, every dX GEMM): the general loop below predicates its bias /
-        // row-group / residual code instead of branching around it (~380 issued instructions per 32-column slab, 60 %
-        // of them predicated off); this copy carries none of it.
+      } else if (g.tma_store && g.epi_plain && !g.rowgroup && !g.residual && g.alpha == 1.f) {
+        // ---- plain bf16 output (QKV projections, every dX GEMM) or bias only (FF / ViT linears): the general loop
+        // below predicates its row-group / residual code instead of branching around it (~380 issued instructions per
+        // 32-column slab, 60 % of them predicated off; a bias alone cost +10 us on 65536 x 320 x 320); this copy carries
+        // only the (warp-uniformly branched) bias add.
         const bool lead_warp = (ew == 0);
         const uint32_t sw = ((uint32_t)row >> 1) & 3u;
         uint32_t v[32];
@@ -249,8 +250,19 @@ e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         for (; c < g.BN && n0 + c < g.N; c += 64) {
           tmem_ld_wait();
           uint32_t w[16];
+          if (g.bias) {   // warp-uniform: Linear / conv bias (fp32, same 32 values for every row: L1 broadcast loads)
 #pragma unroll
-          for (int q = 0; q < 16; ++q) w[q] = pack_bf16(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1]));
+            for (int q = 0; q < 8; ++q) {
+              const int n = n0 + c + q * 4;
+              float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (n + 4 <= g.N) b = *reinterpret_cast<const float4*>(g.bias + n);
+              w[2 * q] = pack_bf16(__uint_as_float(v[4 * q]) + b.x, __uint_as_float(v[4 * q + 1]) + b.y);
+              w[2 * q + 1] = pack_bf16(__uint_as_float(v[4 * q + 2]) + b.z, __uint_as_float(v[4 * q + 3]) + b.w);
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) w[q] = pack_bf16(__uint_as_float(v[2 * q]), __uint_as_float(v[2 * q + 1]));
+          }
           const int cn = c + 64;
           if (cn < g.BN && n0 + cn < g.N) {
             __syncwarp();

@@ -118,13 +118,16 @@ def test_attention_forward_single_key_block_one_vs_two_ctas_per_sm(B, H, N, M, d
 
 @pytest.mark.parametrize("M,N,K,b_mn", [(4096, 960, 320, False), (8192, 320, 320, False), (1000, 328, 192, False),
                                         (4096, 320, 960, True), (256, 64, 64, False)])
-def test_gemm_plain_epilogue_is_bit_identical(M, N, K, b_mn):
+@pytest.mark.parametrize("with_bias", [False, True])
+def test_gemm_plain_epilogue_is_bit_identical(M, N, K, b_mn, with_bias):
+    """The lean epilogue loop (no addend, or a bias only) against the general loop on the same inputs."""
     from e4t_b200 import ops
     g = torch.Generator(device="cuda").manual_seed(M + N + K)
     A = _mk((M, K), g, 0.2)
     Bm = _mk((K, N) if b_mn else (N, K), g, 0.2)
-    y1 = ops.gemm(A, Bm, b_mn=b_mn)
+    bias = torch.randn(N, device="cuda", generator=g) if with_bias else None
+    y1 = ops.gemm(A, Bm, b_mn=b_mn, bias=bias)
     os.environ["E4T_GEMM_EPI_PLAIN"] = "0"
-    y0 = ops.gemm(A, Bm, b_mn=b_mn)
+    y0 = ops.gemm(A, Bm, b_mn=b_mn, bias=bias)
     torch.cuda.synchronize()
     assert torch.equal(y0, y1)
