@@ -234,7 +234,7 @@ e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       const bf16* res = (g.residual && row_ok) ? g.residual + (long long)bz * g.res_bstride + (long long)m * g.ldr
                                                : nullptr;
       if (g.debug & 1) {
-      } else if (g.tma_store && g.epi_plain && !g.rowgroup && !g.residual && g.alpha == 1.f) {
+      } else if (g.tma_store && g.epi_plain && !g.rowgroup && g.alpha == 1.f) {
         // ---- plain bf16 output (QKV projections, every dX GEMM) or bias only (FF / ViT linears): the general loop
         // below predicates its row-group / residual code instead of branching around it (~380 issued instructions per
         // 32-column slab, 60 % of them predicated off; a bias alone cost +10 us on 65536 x 320 x 320); this copy carries
@@ -243,12 +243,41 @@ e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         const uint32_t sw = ((uint32_t)row >> 1) & 3u;
         uint32_t v[32];
         int c = 32 * half;
+        // residual (warp-uniform flag; rows past M read row M-1, their results are clipped by the TMA store): the 64 bytes a
+        // thread needs for a slab are fetched ONE SLAB AHEAD
+        const bool has_res = g.residual != nullptr;
+        const bf16* resc = has_res ? g.residual + (long long)bz * g.res_bstride + (long long)(row_ok ? m : g.M - 1) * g.ldr
+                                   : nullptr;
+        uint4 rv[4];
+        auto load_res = [&](int cc) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int n = n0 + cc + q * 8;
+            rv[q] = (n + 8 <= g.N) ? *reinterpret_cast<const uint4*>(resc + n) : make_uint4(0, 0, 0, 0);
+          }
+        };
         if (c < g.BN && n0 + c < g.N) {
           __syncwarp();
           tmem_ld32(t_row + (uint32_t)c, v);
+          if (has_res) load_res(c);
         }
         for (; c < g.BN && n0 + c < g.N; c += 64) {
           tmem_ld_wait();
+          if (has_res) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float2 r0 = unpack_bf16(rv[q].x), r1 = unpack_bf16(rv[q].y), r2 = unpack_bf16(rv[q].z),
+                           r3 = unpack_bf16(rv[q].w);
+              v[8 * q + 0] = __float_as_uint(__uint_as_float(v[8 * q + 0]) + r0.x);
+              v[8 * q + 1] = __float_as_uint(__uint_as_float(v[8 * q + 1]) + r0.y);
+              v[8 * q + 2] = __float_as_uint(__uint_as_float(v[8 * q + 2]) + r1.x);
+              v[8 * q + 3] = __float_as_uint(__uint_as_float(v[8 * q + 3]) + r1.y);
+              v[8 * q + 4] = __float_as_uint(__uint_as_float(v[8 * q + 4]) + r2.x);
+              v[8 * q + 5] = __float_as_uint(__uint_as_float(v[8 * q + 5]) + r2.y);
+              v[8 * q + 6] = __float_as_uint(__uint_as_float(v[8 * q + 6]) + r3.x);
+              v[8 * q + 7] = __float_as_uint(__uint_as_float(v[8 * q + 7]) + r3.y);
+            }
+          }
           uint32_t w[16];
           if (g.bias) {   // warp-uniform: Linear / conv bias (fp32, same 32 values for every row: L1 broadcast loads)
 #pragma unroll
@@ -267,6 +296,7 @@ e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
           if (cn < g.BN && n0 + cn < g.N) {
             __syncwarp();
             tmem_ld32(t_row + (uint32_t)cn, v);
+            if (has_res) load_res(cn);
           }
           uint8_t* slab = stage_c + (half + 2 * (slab_ctr & 1)) * 8192;
           if (lead_warp) {
@@ -300,18 +330,6 @@ e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
           __syncwarp();
           tmem_ld32(t_row + (uint32_t)c, v);
         }
-        // residual values of the slab, fetched ONE SLAB AHEAD (each thread reads 64 contiguous bytes of its own row: issued
-        // at the point of use the four loads exposed a full memory latency per slab — 60 us against 28 us without the
-        // residual for 65536 x 320 x 320, r02 sweep)
-        uint4 rv[4];
-        auto load_res = [&](int cc) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int n = n0 + cc + q * 8;
-            rv[q] = (res && n + 8 <= g.N) ? *reinterpret_cast<const uint4*>(res + n) : make_uint4(0, 0, 0, 0);
-          }
-        };
-        if (any) load_res(c);
         for (; c < g.BN && n0 + c < g.N; c += 64) {
           tmem_ld_wait();
           uint32_t w[16];
@@ -334,9 +352,10 @@ e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
                 f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
               }
-              if (res) {
-                const float2 r0 = unpack_bf16(rv[q].x), r1 = unpack_bf16(rv[q].y), r2 = unpack_bf16(rv[q].z),
-                             r3 = unpack_bf16(rv[q].w);
+              if (res) {   // (only with a row-group addend or alpha != 1: every other residual goes through the lean loop)
+                const uint4 rvq = *reinterpret_cast<const uint4*>(res + n);
+                const float2 r0 = unpack_bf16(rvq.x), r1 = unpack_bf16(rvq.y), r2 = unpack_bf16(rvq.z),
+                             r3 = unpack_bf16(rvq.w);
                 f[0] += r0.x; f[1] += r0.y; f[2] += r1.x; f[3] += r1.y;
                 f[4] += r2.x; f[5] += r2.y; f[6] += r3.x; f[7] += r3.y;
               }
@@ -351,7 +370,6 @@ e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
           if (cn < g.BN && n0 + cn < g.N) {
             __syncwarp();
             tmem_ld32(t_row + (uint32_t)cn, v);
-            load_res(cn);
           }
           if (g.debug & 4) continue;
           // this half cycles through staging slabs {half, half + 2}
