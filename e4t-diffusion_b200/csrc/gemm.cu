@@ -234,7 +234,7 @@ e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
       const bf16* res = (g.residual && row_ok) ? g.residual + (long long)bz * g.res_bstride + (long long)m * g.ldr
                                                : nullptr;
       if (g.debug & 1) {
-      } else if (g.tma_store && g.epi_plain && !g.rowgroup && g.alpha == 1.f) {
+      } else if (g.tma_store && g.epi_plain && g.alpha == 1.f) {
         // ---- plain bf16 output (QKV projections, every dX GEMM) or bias only (FF / ViT linears): the general loop
         // below predicates its row-group / residual code instead of branching around it (~380 issued instructions per
         // 32-column slab, 60 % of them predicated off; a bias alone cost +10 us on 65536 x 320 x 320); this copy carries
@@ -276,6 +276,20 @@ e4t_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
               v[8 * q + 5] = __float_as_uint(__uint_as_float(v[8 * q + 5]) + r2.y);
               v[8 * q + 6] = __float_as_uint(__uint_as_float(v[8 * q + 6]) + r3.x);
               v[8 * q + 7] = __float_as_uint(__uint_as_float(v[8 * q + 7]) + r3.y);
+            }
+          }
+          if (g.rowgroup) {   // warp-uniform flag: per-image time-embedding row of ResnetBlock2D.conv1 (fp32 [M / rpg][N])
+            const float* rgr = g.rowgroup + (long long)((row_ok ? m : g.M - 1) / g.rows_per_group) * g.N;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const int n = n0 + c + q * 4;
+              if (n + 4 <= g.N) {
+                const float4 b = *reinterpret_cast<const float4*>(rgr + n);
+                v[4 * q + 0] = __float_as_uint(__uint_as_float(v[4 * q + 0]) + b.x);
+                v[4 * q + 1] = __float_as_uint(__uint_as_float(v[4 * q + 1]) + b.y);
+                v[4 * q + 2] = __float_as_uint(__uint_as_float(v[4 * q + 2]) + b.z);
+                v[4 * q + 3] = __float_as_uint(__uint_as_float(v[4 * q + 3]) + b.w);
+              }
             }
           }
           uint32_t w[16];
