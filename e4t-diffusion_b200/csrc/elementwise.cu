@@ -809,13 +809,23 @@ extern "C" int e4t_wo_bank_fwd(const void* tab, int n, int max_r, int max_c, voi
 }
 // fac_bw: pointer to the start of the (contiguous) factor scratch of the whole bank and its size in floats: the
 // backward sub-ranges that need zeroing (GTb, GTs, dvx, dvy) are zeroed by clearing every projection's backward area.
-extern "C" int e4t_wo_bank_bwd(const void* tab, int n, int max_r, int max_c, float* bw_base, long long bw_floats,
-                               void* stream_) {
+// Phase 1: G reductions.  bw of every projection then holds Ga[C] Gbc[C] G1[C] GTb[R] GTs[R] (and zeros for dvx, dvy).
+// Everything after this point is LINEAR in these five vectors with coefficients that depend on the parameters only, so a
+// data-parallel run may all-reduce the (contiguous, ~2 MB) bw buffer here instead of the 573 MB of parameter gradients.
+extern "C" int e4t_wo_bank_bwd_reduce(const void* tab, int n, int max_r, int max_c, float* bw_base, long long bw_floats,
+                                      void* stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   const WOProj* t = (const WOProj*)tab;
   E4T_CUDA(cudaMemsetAsync(bw_base, 0, (size_t)bw_floats * sizeof(float), st));
   wo_bank_reduce_kernel<<<dim3(cdiv(max_c, 8), n), 256, (size_t)2 * max_r * sizeof(float), st>>>(t);
   E4T_COUNT_LAUNCH();
+  E4T_LAUNCH_CHECK();
+  return 0;
+}
+// Phase 2: parameter gradients from the (possibly all-reduced) five vectors, accumulated into the .grad views.
+extern "C" int e4t_wo_bank_bwd_apply(const void* tab, int n, int max_r, int max_c, void* stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  const WOProj* t = (const WOProj*)tab;
   const int mx = max_r > max_c ? max_r : max_c;
   wo_bank_colmatvec_kernel<<<dim3(cdiv(mx, 128), cdiv(mx, 32), 2 * n), 128, 0, st>>>(t);
   E4T_COUNT_LAUNCH();
@@ -825,5 +835,10 @@ extern "C" int e4t_wo_bank_bwd(const void* tab, int n, int max_r, int max_c, flo
   E4T_COUNT_LAUNCH();
   E4T_LAUNCH_CHECK();
   return 0;
+}
+extern "C" int e4t_wo_bank_bwd(const void* tab, int n, int max_r, int max_c, float* bw_base, long long bw_floats,
+                               void* stream_) {
+  if (int e = e4t_wo_bank_bwd_reduce(tab, n, max_r, max_c, bw_base, bw_floats, stream_)) return e;
+  return e4t_wo_bank_bwd_apply(tab, n, max_r, max_c, stream_);
 }
 extern "C" int e4t_wo_bank_record_size(void) { return (int)sizeof(WOProj); }

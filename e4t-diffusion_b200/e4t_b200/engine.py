@@ -186,6 +186,7 @@ class PretrainStep:
                              weight_decay=weight_decay, eps=eps) if optimizer else None
         self._graph = None
         self.wo_bank = None
+        self._wo_factor_exchange = False
         # Data parallel: the encoder-head gradients (925 MB of the 1.5 GB arena, an arena prefix) are final as soon as
         # the head's backward has run — before the encoder-half UNet backward.  Their all-reduce is issued at that
         # moment on a communication stream and overlaps that backward; only the WeightOffsets slice (produced by the
@@ -206,6 +207,15 @@ class PretrainStep:
             self.wo_bank = WOBank(attns)
             for m in attns:
                 m._wo_bank = self.wo_bank
+            # Data parallel, head slice exchanged early, and everything behind it in the arena is WeightOffsets
+            # parameters: the bank exchanges its ~2 MB of G reductions inside backward and the 573 MB parameter-gradient
+            # slice is never all-reduced (E4T_WO_FACTOR_EXCHANGE=0 keeps the slice exchange).
+            self._wo_factor_exchange = False
+            if self._early_end is not None and os.environ.get("E4T_WO_FACTOR_EXCHANGE", "1") != "0":
+                rest = {i for i, (o, n) in self.opt.offsets.items() if o >= self._early_end}
+                if rest == {id(p) for p in self.wo_bank.params}:
+                    self.wo_bank.dp_group = True
+                    self._wo_factor_exchange = True
 
     def placeholder_idxs(self, input_ids):
         """[ids.index(placeholder_id) for ids in input_ids] (pretrain_e4t.py:617) — exact integer bookkeeping."""
@@ -348,8 +358,13 @@ class PretrainStep:
         if self.opt is not None:
             if self._early_fired:
                 torch.cuda.current_stream().wait_stream(self._comm)
-                scale = self.opt.all_reduce_grads(self._early_end, None)
+                if self._wo_factor_exchange:      # the bank summed its gradients over the ranks inside backward
+                    scale = 1.0 / dist.get_world_size()
+                else:
+                    scale = self.opt.all_reduce_grads(self._early_end, None)
                 self._early_fired = False
+            elif self._wo_factor_exchange:        # head hook did not fire: its slice still needs the exchange, the bank's does not
+                scale = self.opt.all_reduce_grads(0, self._early_end)
             else:
                 scale = self.opt.all_reduce_grads()
             if self.max_grad_norm is not None:

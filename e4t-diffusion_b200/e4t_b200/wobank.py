@@ -89,6 +89,7 @@ class WOBank:
         self._table = None
         self._token = None
         self._key = None
+        self.dp_group = None      # set by engine.PretrainStep under data parallelism: exchange the G reductions (see _launch_backward)
         assert _lib.load().e4t_wo_bank_record_size() == ctypes.sizeof(_WOProj)
         for m in self.modules:      # any (partial) load_state_dict invalidates the cached W_eff
             m.register_load_state_dict_post_hook(lambda mod, keys: FN.bump_param_epoch())
@@ -129,8 +130,20 @@ class WOBank:
                   stream())
 
     def _launch_backward(self):
-        _lib.call("e4t_wo_bank_bwd", ptr(self._table), c_int(len(self.projs)), c_int(self.max_r), c_int(self.max_c),
-                  ptr(self.bw), c_ll(self.bw.numel()), stream())
+        if self.dp_group is None:
+            _lib.call("e4t_wo_bank_bwd", ptr(self._table), c_int(len(self.projs)), c_int(self.max_r), c_int(self.max_c),
+                      ptr(self.bw), c_ll(self.bw.numel()), stream())
+            return
+        # data parallel (engine.PretrainStep): exchange the five G reductions of every projection (~2 MB) instead of the
+        # 573 MB of WeightOffsets parameter gradients they expand to — every later step of the backward is linear in
+        # them with rank-identical coefficients, so each rank then accumulates the SUM over ranks into its .grad views
+        # (the 1/world average is folded into the optimiser like for the rest of the arena)
+        import torch.distributed as dist
+        _lib.call("e4t_wo_bank_bwd_reduce", ptr(self._table), c_int(len(self.projs)), c_int(self.max_r),
+                  c_int(self.max_c), ptr(self.bw), c_ll(self.bw.numel()), stream())
+        dist.all_reduce(self.bw, op=dist.ReduceOp.SUM, group=None if self.dp_group is True else self.dp_group)
+        _lib.call("e4t_wo_bank_bwd_apply", ptr(self._table), c_int(len(self.projs)), c_int(self.max_r),
+                  c_int(self.max_c), stream())
 
     # ---- per-step access ------------------------------------------------------------------------------------------
     def get(self, module, group):

@@ -169,6 +169,11 @@ int e4t_wo_bwd(const float* dWeff, const float* W, const float* v, const float* 
  * pointers.  fwd = 2 launches (factors, W_eff); bwd = 4 launches + one memset of the backward scratch. */
 int e4t_wo_bank_fwd(const void* tab, int n, int max_r, int max_c, void* stream);
 int e4t_wo_bank_bwd(const void* tab, int n, int max_r, int max_c, float* bw_base, long long bw_floats, void* stream);
+/* The same in two phases, for data-parallel runs: _reduce leaves the five G reductions of every projection in bw
+ * (contiguous, ~2 MB for SD-v1.4); the caller all-reduces bw; _apply expands them into the parameter gradients
+ * (every later step is linear in them with rank-identical coefficients). */
+int e4t_wo_bank_bwd_reduce(const void* tab, int n, int max_r, int max_c, float* bw_base, long long bw_floats, void* stream);
+int e4t_wo_bank_bwd_apply(const void* tab, int n, int max_r, int max_c, void* stream);
 int e4t_wo_bank_record_size(void);
 
 /* ---- optimiser (torch.optim.AdamW at pretrain_e4t.py:389-392,652) ---------------------------------------------- */
