@@ -162,6 +162,51 @@ def test_pretrain_step_tiny_vs_oracle_and_loss_curve():
         assert abs(lo[2] - lg[2]) <= 3e-2 * abs(lo[2]) + 1e-6, (lo, lg)
 
 
+def test_wo_bank_two_phase_backward_is_linear_in_the_reductions():
+    """Data-parallel exchange of the WeightOffsets bank (engine.PretrainStep: all-reduce of the ~2 MB of G reductions
+    instead of the parameter gradients).  Emulated on one GPU: the parameter gradients of two different dW_eff (two
+    "ranks"), computed separately and summed, must equal ONE apply phase over the sum of the two reduce-phase buffers."""
+    from ctypes import c_int, c_longlong
+    from e4t_b200 import _lib
+    from e4t_b200._lib import ptr, stream
+    unet, enc, text, _, (ucfg, vcfg, tcfg), PretrainStep = _build_step(seed=5)
+    step = PretrainStep(unet, enc, text, O.PLACEHOLDER_ID, class_token_id=320, lr=1e-3, weight_dtype=torch.float32)
+    bank = step.wo_bank
+    bank._launch_forward()
+    torch.cuda.synchronize()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    G = [torch.randn(bank.dweff.shape, device="cuda", generator=g) for _ in range(2)]
+    grads = [p.grad for p in bank.params]
+
+    def snapshot():
+        return torch.cat([x.detach().flatten().clone() for x in grads])
+
+    def zero():
+        for x in grads:
+            x.zero_()
+
+    n, mr, mc = c_int(len(bank.projs)), c_int(bank.max_r), c_int(bank.max_c)
+    separate = []
+    for k in range(2):
+        zero()
+        bank.dweff.copy_(G[k])
+        _lib.call("e4t_wo_bank_bwd", ptr(bank._table), n, mr, mc, ptr(bank.bw), c_longlong(bank.bw.numel()), stream())
+        separate.append(snapshot())
+    zero()
+    bws = []
+    for k in range(2):
+        bank.dweff.copy_(G[k])
+        _lib.call("e4t_wo_bank_bwd_reduce", ptr(bank._table), n, mr, mc, ptr(bank.bw), c_longlong(bank.bw.numel()), stream())
+        bws.append(bank.bw.clone())
+    bank.bw.copy_(bws[0] + bws[1])                    # what the all-reduce(SUM) over two ranks leaves in the buffer
+    _lib.call("e4t_wo_bank_bwd_apply", ptr(bank._table), n, mr, mc, stream())
+    fused = snapshot()
+    torch.cuda.synchronize()
+    ref = separate[0] + separate[1]
+    assert ref.abs().max() > 0
+    assert _rel(fused, ref) < 1e-5, _rel(fused, ref)
+
+
 def test_state_dict_roundtrip_and_checkpoint_contract(tmp_path):
     from e4t import utils
     unet, enc, text, sds, cfgs, _ = _build_step(seed=3)
