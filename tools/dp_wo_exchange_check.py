@@ -1,7 +1,11 @@
 """2-GPU check of the WeightOffsets factor exchange (engine.PretrainStep under data parallelism): two eager steps with
 per-rank batches; rank 0 writes the trained-parameter arena's WeightOffsets slice, the head slice checksum and the losses.
 Run once with E4T_WO_FACTOR_EXCHANGE=1 and once with =0 (slice all-reduce) and compare the files:
-    torchrun --nproc-per-node 2 tools/dp_wo_exchange_check.py out.pt ;  python tools/dp_wo_exchange_check.py --compare a.pt b.pt"""
+    torchrun --nproc-per-node 2 tools/dp_wo_exchange_check.py out.pt ;  python tools/dp_wo_exchange_check.py --compare a.pt b.pt
+NOTE (round-2 call 31): comparing PARAMETERS after AdamW steps is ill-conditioned — the first Adam update is lr * sign(g),
+so run-to-run rounding noise of near-zero gradients (fp32 atomics) moves entries by 2 lr: the encoder-head sample, which
+the exchange mode does not touch, differed by the same 3e-3 as the WeightOffsets slice (step-1 losses equal to 1e-7).  The
+exact check of the exchange is tests/test_e2e_gpu.py::test_wo_bank_two_phase_backward_is_linear_in_the_reductions."""
 import os
 import sys
 
@@ -16,8 +20,8 @@ def compare(a, b):
     relh = ((x["head"] - y["head"]).norm() / y["head"].norm()).item()
     print(f"WO slice after 2 steps: rel diff {rel:.3e} (max abs {(x['wo'] - y['wo']).abs().max().item():.3e}); "
           f"head sample rel diff {relh:.3e}; losses {x['loss']} vs {y['loss']}; flags {x['flag']} vs {y['flag']}")
-    ok = rel < 1e-5 and relh < 1e-5
-    print("FACTOR EXCHANGE OK" if ok else "FACTOR EXCHANGE MISMATCH")
+    ok = abs(x["loss"][0] - y["loss"][0]) < 1e-4 * abs(y["loss"][0]) and rel < 3 * max(relh, 1e-6)
+    print("consistent (WeightOffsets slice differs no more than the untouched head slice)" if ok else "MISMATCH")
     return 0 if ok else 1
 
 
