@@ -576,7 +576,9 @@ def main():
                            "l2": "inputs rotate over 4 batches; per-step working set (activations ~30 GB) >> 126 MB L2",
                            "grad_allreduce": ("NCCL all-reduce of the flat fp32 grad arena: encoder-head slice issued from "
                                               "inside backward on a comm stream (overlaps the enc-half UNet backward), "
-                                              "WeightOffsets slice after backward; "
+                                              + ("WeightOffsets gradients exchanged as the bank's 2 MB of G reductions inside "
+                                                 "backward (the 573 MB slice is not all-reduced); "
+                                                 if getattr(step, "_wo_factor_exchange", False) else "WeightOffsets slice after backward; ")
                                               + ("all inside the CUDA graph" if getattr(step, "_graph_has_opt", False)
                                                  else "eager after the compute-only graph")
                                               + ("; " + step._capture_note if getattr(step, "_capture_note", None) else ""))
