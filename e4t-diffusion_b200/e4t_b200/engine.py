@@ -293,6 +293,7 @@ class PretrainStep:
                 self._capture_note = f"NCCL-in-graph capture failed ({type(ex).__name__}: {str(ex)[:120]}); compute-only graph"
                 self._early_fired = False
                 self._comm = None               # no collective inside the compute-only graph
+                self._disable_wo_factor_exchange()
                 torch.cuda.synchronize()
                 self._drop_autograd_refs()
                 gc.collect()
@@ -300,6 +301,7 @@ class PretrainStep:
                 graph = capture(self._fwd_bwd, "thread_local")
         elif multi:
             self._comm = None
+            self._disable_wo_factor_exchange()
             self._graph_has_opt = False
             graph = capture(self._fwd_bwd, "thread_local")
         else:
@@ -307,6 +309,13 @@ class PretrainStep:
         self._drop_autograd_refs()
         self._graph = graph
         return self
+
+    def _disable_wo_factor_exchange(self):
+        """Compute-only graph (no collective may be captured): the bank's in-backward all-reduce goes too; the
+        WeightOffsets slice is then exchanged with the rest of the arena after the graph."""
+        if self.wo_bank is not None:
+            self.wo_bank.dp_group = None
+        self._wo_factor_exchange = False
 
     def release_cuda_graph(self):
         """Drop the captured step (and its static buffers).  Call before `dist.destroy_process_group()`: a live graph
