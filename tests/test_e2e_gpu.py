@@ -204,7 +204,7 @@ def test_wo_bank_two_phase_backward_is_linear_in_the_reductions():
     torch.cuda.synchronize()
     ref = separate[0] + separate[1]
     assert ref.abs().max() > 0
-    assert _rel(fused, ref) < 1e-5, _rel(fused, ref)
+    assert _rel(fused, ref) < 1e-4, _rel(fused, ref)      # fp32 association only (a bug here is an O(1) error)
 
 
 def test_state_dict_roundtrip_and_checkpoint_contract(tmp_path):
